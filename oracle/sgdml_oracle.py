@@ -1,0 +1,462 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU (numpy/scipy) restatement of the reference's solve path.
+
+This module is the parity checker for the CUDA path.  Only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it; the product package
+(``mlff_preconditioner_b200``) never does and has no CPU fallback.
+
+Parity status: PINNED against the reference itself.  The reference ships no tests or golden
+vectors, so every function below was checked against the *unmodified*
+reference code imported in the build container (``oracle/ref_shims.py``) on seeded synthetic
+inputs; the resulting vectors are frozen in ``tests/golden/*.npz`` by
+``tests/golden/make_golden.py`` and re-checked on every CPU test run
+(``tests/test_oracle_golden.py``).  Third-party arithmetic at the reference's call sites
+(scipy 1.7.3 ``cg``/``cholesky``/``solve_triangular``/``cho_factor``/``eigh``, numpy ``einsum``/``argmax``,
+torch 1.13.1 ``einsum``/``mm``/``exp``/``norm``; ``/root/reference/environment.yml:6-14``) is not vendored;
+their published algorithms are restated here (legacy ``cg`` semantics in :func:`pcg`).
+
+All paths cited below are relative to ``/root/reference/src/sGDML/sgdml/``.
+Notation: N atoms, D = N(N-1)/2, S perms, M training points, n = 3NM.
+"""
+import numpy as np
+import scipy.linalg
+
+
+# --------------------------------------------------------------------------------------
+# descriptor algebra (utils/desc.py)
+# --------------------------------------------------------------------------------------
+def n_atoms_from_dim_d(dim_d):
+    """train.py:128."""
+    return int((1 + np.sqrt(8 * dim_d + 1)) / 2)
+
+
+def inflate_jacobian(r_d_desc):
+    """Dense ``J[D, 3N]`` from the compressed ``g[D,3]``: ``J[d, b_d] = +g_d``, ``J[d, a_d] = -g_d``
+    with (a_d, b_d) = tril_indices rows/cols (utils/desc.py:444-462)."""
+    dim_d = r_d_desc.shape[0]
+    n_atoms = n_atoms_from_dim_d(dim_d)
+    a, b = np.tril_indices(n_atoms, k=-1)
+    J = np.zeros((dim_d, n_atoms, 3))
+    J[np.arange(dim_d), b, :] = r_d_desc
+    J[np.arange(dim_d), a, :] = -r_d_desc
+    return J.reshape(dim_d, 3 * n_atoms)
+
+
+def d_desc_dot_vec(R_d_desc, vecs):
+    """``beta[m,d] = g[m,d,:] . (v[m,b_d,:] - v[m,a_d,:])``  (utils/desc.py:394-405)."""
+    n_atoms = n_atoms_from_dim_d(R_d_desc.shape[1])
+    a, b = np.tril_indices(n_atoms, k=-1)
+    v = vecs.reshape(R_d_desc.shape[0], n_atoms, 3)
+    return np.einsum('kji,kji->kj', R_d_desc, v[:, b, :] - v[:, a, :])
+
+
+def vec_dot_d_desc(R_d_desc, f):
+    """``F[m, b_d] += g_d f_d ; F[m, a_d] -= g_d f_d``  (utils/desc.py:408-428).
+    Note the reference writes ``out[i,j] = g f`` with i = rows (a), j = cols (b) and sums over
+    axis 1 (the first atom index), so atom b receives +, atom a receives -."""
+    M, dim_d = R_d_desc.shape[:2]
+    n_atoms = n_atoms_from_dim_d(dim_d)
+    a, b = np.tril_indices(n_atoms, k=-1)
+    gf = R_d_desc * f[..., None]
+    out = np.zeros((M, n_atoms, 3))
+    np.add.at(out, (slice(None), b), gf)
+    np.add.at(out, (slice(None), a), -gf)
+    return out.reshape(M, -1)
+
+
+def desc_perms(tril_perms_lin, dim_d):
+    """``pi[p, d]`` from ``tril_perms_lin[d*S + p] = pi_p(d) + p*D``  (train.py:783-790)."""
+    S = len(tril_perms_lin) // dim_d
+    return np.asarray(tril_perms_lin).reshape(dim_d, S).T - (np.arange(S) * dim_d)[:, None]
+
+
+def permuted_rows(X, tril_perms_lin):
+    """``X[m, pi_p(d)]`` stacked as ``[M, S, D]`` (row m*S+p of the reference's ``[M*S, D]`` layout,
+    predict.py:347-351, torchtools.py:82-97, train.py:151-153)."""
+    pi = desc_perms(tril_perms_lin, X.shape[1])
+    return X[:, pi]  # [M, S, D]
+
+
+# --------------------------------------------------------------------------------------
+# explicit kernel (train.py:81-236, 1121-1308)
+# --------------------------------------------------------------------------------------
+def _column_plan(col_idxs, n_train, dim_i):
+    """(panel start, point j, kept Cartesian indices) tuples  (train.py:1237-1263)."""
+    if col_idxs is None:
+        return [(j * dim_i, j, np.arange(dim_i)) for j in range(n_train)], n_train * dim_i
+    col_idxs = np.asarray(col_idxs)
+    assert len(col_idxs) == len(set(col_idxs.tolist()))  # train.py:1197
+    assert np.array_equal(col_idxs, np.sort(col_idxs))  # train.py:1201
+    n_idxs = np.mod(col_idxs, dim_i)
+    m_idxs = (col_idxs / dim_i).astype(int)
+    plan, start = [], 0
+    for m in np.unique(m_idxs):
+        keep = n_idxs[m_idxs == m]
+        plan.append((start, int(m), keep))
+        start += len(keep)
+    return plan, len(col_idxs)
+
+
+def assemble_kernel_mat(R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=None):
+    """Explicit Hessian-Matern-5/2 kernel ``K[n, n_cols]`` (negative semidefinite).
+
+    Follows ``_assemble_kernel_mat_wkr`` (train.py:150-205), vectorised over the row points i:
+    for a column point j with permuted copies ``x_j^(p)``, ``J_j^(p)``::
+
+        diff = x_i - x_j^(p);  rho = sqrt5 |diff|;  base = 5 exp(-rho/sig) / (3 sig^4)
+        outer = 5 * sum_p (diff base)[d] (diff . J_j^(p))[r]  -  sum_p J_j^(p)[d,r] (sig^2 + sig rho) base
+        K[blk_i, blk_j] = J_i^T outer
+    """
+    M, D = R_desc.shape
+    N = n_atoms_from_dim_d(D)
+    dim_i = 3 * N
+    pi = desc_perms(tril_perms_lin, D)  # [S, D]
+    plan, n_cols = _column_plan(col_idxs, M, dim_i)
+    K = np.zeros((M * dim_i, n_cols))
+    J_all = np.stack([inflate_jacobian(R_d_desc[i]) for i in range(M)])  # [M, D, 3N]
+    sqrt5 = np.sqrt(5.0)
+    mat52_base_div = 3 * sig ** 4
+    for start, j, keep in plan:
+        xjp = R_desc[j][pi]  # [S, D]
+        Jjp = J_all[j][:, keep][pi]  # [S, D, keep]   rows permuted, Cartesian columns untouched
+        diff = R_desc[:, None, :] - xjp[None]  # [M, S, D]
+        norm = sqrt5 * np.linalg.norm(diff, axis=2)  # [M, S]
+        base = np.exp(-norm / sig) / mat52_base_div * 5
+        inner = np.einsum('isd,sdr->isr', diff, Jjp)
+        outer = 5 * np.einsum('isd,isr->idr', diff * base[..., None], inner)
+        outer -= np.einsum('sdr,is->idr', Jjp, (sig ** 2 + sig * norm) * base)
+        blk = np.einsum('idq,idr->iqr', J_all, outer)  # [M, 3N, keep]
+        K[:, start:start + len(keep)] = blk.reshape(M * dim_i, len(keep))
+    return K
+
+
+def kernel_mat_diag(R_desc, R_d_desc, tril_perms_lin, sig):
+    """``-diag(K)`` (positive) from the i = j blocks only  (solvers/iterative_cholesky.py:241-373)."""
+    M, D = R_desc.shape
+    N = n_atoms_from_dim_d(D)
+    dim_i = 3 * N
+    pi = desc_perms(tril_perms_lin, D)
+    sqrt5 = np.sqrt(5.0)
+    out = np.zeros(M * dim_i)
+    for j in range(M):
+        Jj = inflate_jacobian(R_d_desc[j])
+        xjp, Jjp = R_desc[j][pi], Jj[pi]
+        diff = R_desc[j][None] - xjp
+        norm = sqrt5 * np.linalg.norm(diff, axis=1)
+        base = np.exp(-norm / sig) / (3 * sig ** 4) * 5
+        outer = 5 * np.einsum('sd,sr->dr', diff * base[:, None], np.einsum('sd,sdr->sr', diff, Jjp))
+        outer -= np.einsum('sdr,s->dr', Jjp, (sig ** 2 + sig * norm) * base)
+        out[j * dim_i:(j + 1) * dim_i] = np.einsum('dq,dq->q', Jj, outer)
+    return -out
+
+
+# --------------------------------------------------------------------------------------
+# matrix-free operator (torchtools.py:128-151,172-272; predict.py:172-229; iterative_solver.py:416-443)
+# --------------------------------------------------------------------------------------
+def kernel_matvec(R_desc, R_d_desc, tril_perms_lin, sig, v, chunk=64):
+    """``K v`` without forming K.
+
+    ``beta_j = J_j v_j`` (torchtools.py:145), permuted copies stacked ``[M*S, D]`` (:148-151); for query i::
+
+        x_diffs = q (x_i - x_j^(p)), q = sqrt5/sig;  x_dists = |x_diffs|
+        exp_xs  = 5/(3 sig^2) exp(-x_dists)
+        f_i = sum_jp exp_xs (x_diffs . beta) x_diffs - sum_jp exp_xs (1 + x_dists) beta     (:216-248)
+        (K v)_i = J_i^T f_i                                                                  (:259-263)
+    """
+    M, D = R_desc.shape
+    q = np.sqrt(5) / sig
+    beta = d_desc_dot_vec(R_d_desc, np.asarray(v, dtype=float).reshape(M, -1))
+    Xp = permuted_rows(R_desc, tril_perms_lin).reshape(-1, D)
+    Bp = permuted_rows(beta, tril_perms_lin).reshape(-1, D)
+    Fs_x = np.empty((M, D))
+    for s in range(0, M, chunk):
+        x_diffs = (q * R_desc[s:s + chunk])[:, None, :] - q * Xp[None]
+        x_dists = np.linalg.norm(x_diffs, axis=-1)
+        exp_xs = 5.0 / (3 * sig ** 2) * np.exp(-x_dists)
+        dot = np.einsum('ijk,jk->ij', x_diffs, Bp)
+        f = np.einsum('ij,ijk->ik', exp_xs * dot, x_diffs)
+        f -= (exp_xs * (1 + x_dists)).dot(Bp)
+        Fs_x[s:s + chunk] = f
+    return vec_dot_d_desc(R_d_desc, Fs_x).ravel()
+
+
+def kernel_matvec_torch_cpu(R_desc_t, Xp_t, R_d_desc, tril_perms_lin, sig, v, batch=256):
+    """Same operator with torch-CPU ops (the reference's fastest CPU route, ``use_torch=True`` with no
+    GPU visible: torchtools.py:64,172-272) -- used only to time the CPU baseline with all host threads."""
+    import torch
+
+    M, D = R_desc_t.shape
+    q = np.sqrt(5) / sig
+    beta = d_desc_dot_vec(R_d_desc, np.asarray(v, dtype=float).reshape(M, -1))  # host numpy, as torchtools.py:145
+    Bp = torch.from_numpy(permuted_rows(beta, tril_perms_lin).reshape(-1, D))
+    out = torch.empty((M, D), dtype=torch.float64)
+    for s in range(0, M, batch):
+        x_diffs = (q * R_desc_t[s:s + batch])[:, None, :] - q * Xp_t
+        x_dists = x_diffs.norm(dim=-1)
+        exp_xs = 5.0 / (3 * sig ** 2) * torch.exp(-x_dists)
+        dot = torch.einsum('ijk,jk->ij', x_diffs, Bp)
+        f = torch.einsum('ij,ij,ijk->ik', exp_xs, dot, x_diffs)
+        f -= (exp_xs * (1 + x_dists)).mm(Bp)
+        out[s:s + batch] = f
+    return vec_dot_d_desc(R_d_desc, out.numpy()).ravel()
+
+
+def kernel_operator(R_desc, R_d_desc, tril_perms_lin, sig, lam):
+    """``v -> K v - lam v``  (iterative_solver.py:438-443).  CG is run on its negative."""
+
+    def K_op(v):
+        return kernel_matvec(R_desc, R_d_desc, tril_perms_lin, sig, v) - lam * v
+
+    return K_op
+
+
+# --------------------------------------------------------------------------------------
+# pivoted partial Cholesky (solvers/incomplete_cholesky.py:24-93)
+# --------------------------------------------------------------------------------------
+def pivoted_cholesky(get_col, diagonal, max_rank, forced_pivots=None, return_gaps=False):
+    """Greedy diagonal-pivoted partial Cholesky.
+
+    Step m (incomplete_cholesky.py:50-78): ``i* = argmax(diag[index_columns][m:]) + m`` (first maximum
+    in the current permuted order), swap positions m and i*, ``pi = index_columns[m]``,
+    ``L[pi,m] = sqrt(diag[pi])`` (assert > 0), ``c = get_col(pi)``,
+    ``L[rest,m] = (c[rest] - L[rest,:m] . L[pi,:m]) / L[pi,m]``, ``diag[rest] -= L[rest,m]^2``.
+
+    ``forced_pivots`` (test protocol) replays a given pivot sequence;
+    ``return_gaps`` also returns the relative gap between the two largest candidates per step.
+    """
+    diag = np.array(diagonal, dtype=float)
+    n = diag.size
+    assert max_rank <= n, f'max_rank = {max_rank} is too large'
+    index_columns = np.arange(n)
+    L = np.zeros((n, max_rank))
+    gaps = np.zeros(max_rank)
+    for m in range(max_rank):
+        cand = diag[index_columns][m:]
+        if forced_pivots is None:
+            i_argmax = int(np.argmax(cand) + m)
+        else:
+            i_argmax = int(np.where(index_columns == forced_pivots[m])[0][0])
+        if return_gaps and cand.size > 1:
+            top2 = np.partition(cand, -2)[-2:]
+            gaps[m] = (top2[1] - top2[0]) / abs(top2[1])
+        index_columns[m], index_columns[i_argmax] = index_columns[i_argmax], index_columns[m]
+        m_pi = index_columns[m]
+        i_pi = index_columns[m + 1:]
+        pivot_element = diag[m_pi]
+        assert pivot_element > 0, 'given matrix is not PSD'
+        L[m_pi, m] = np.sqrt(pivot_element)
+        col = get_col(m_pi)
+        schur = 0
+        if m > 0:
+            schur = np.einsum('c,rc->r', L[m_pi, :m], L[i_pi, :m])
+        L[i_pi, m] = (col[i_pi] - schur) / L[m_pi, m]
+        diag[i_pi] -= L[i_pi, m] ** 2
+    if return_gaps:
+        return L, index_columns, gaps
+    return L, index_columns
+
+
+# --------------------------------------------------------------------------------------
+# Woodbury / Nystroem preconditioners
+# --------------------------------------------------------------------------------------
+def woodbury_factor(L, lam):
+    """``T = chol_lower(lam I_k + L^T L)^{-1} L^T``  ``[k, n]``  (solvers/iterative_cholesky.py:141-143)."""
+    k = L.shape[1]
+    kernel = lam * np.eye(k) + (L.T @ L)
+    L2 = scipy.linalg.cholesky(kernel, lower=True)
+    return scipy.linalg.solve_triangular(L2, L.T, lower=True)
+
+
+def woodbury_apply(T, lam, a):
+    """``(a - T^T (T a)) / lam``  (solvers/iterative_cholesky.py:145-148)."""
+    return (1.0 / lam) * (a - T.T @ (T @ a))
+
+
+def cho_factor_stable(Mat):
+    """Upper Cholesky factor after the +-1e-15 diagonal nudge (solvers/iterative_solver.py:576-583).
+    Returns the clean upper-triangular factor (the reference keeps LAPACK's full array + a flag)."""
+    Mat = np.array(Mat, dtype=float)
+    lo_eig = scipy.linalg.eigh(Mat, eigvals_only=True, subset_by_index=[0, 0])
+    sgn = 1 if lo_eig <= 0 else -1
+    Mat[np.diag_indices_from(Mat)] += sgn * 1.0e-15
+    return scipy.linalg.cholesky(Mat, lower=False)
+
+
+def nystrom_factor(K_nm, idxs, lam):
+    """``B[m, n]`` with ``P v = (B^T (B v) - v)/lam``  (solvers/iterative_solver.py:112-322):
+    ``U = chol_upper(-K_mm +- 1e-15 I)``; ``Kt = K_nm U^{-1}``; ``U2 = chol_upper(Kt^T Kt + lam I +- 1e-15 I)``;
+    ``B = (Kt U2^{-1})^T``."""
+    K_mm = K_nm[idxs, :]
+    U = cho_factor_stable(-K_mm)
+    Kt = scipy.linalg.solve_triangular(U, K_nm.T, lower=False, trans='T').T
+    inner = Kt.T.dot(Kt)
+    inner[np.diag_indices_from(inner)] += lam
+    U2 = cho_factor_stable(inner)
+    Kt = scipy.linalg.solve_triangular(U2, Kt.T, lower=False, trans='T').T
+    return Kt.T
+
+
+def nystrom_apply(B, lam, v):
+    """``(B^T (B v) - v) / lam`` -- the *negative* Woodbury inverse (solvers/iterative_solver.py:315-318)."""
+    return (B.T.dot(B.dot(v)) - v) * (1.0 / lam)
+
+
+def nystrom_factor_sb(K_nm_neg, idxs, lam):
+    """``_init_precon_operator_sb`` (solvers/iterative_solver.py:343-381); input is ``-K[:, idxs]``.
+    Returns P_invers [m, n]; apply is ``-(a - P^T P a)/lam``."""
+    m = K_nm_neg.shape[1]
+    K_mm = K_nm_neg[idxs, :]
+    L_m = scipy.linalg.cholesky(K_mm + 1e-16 * np.eye(m), lower=True)
+    Kbar = scipy.linalg.solve_triangular(L_m, K_nm_neg.T, lower=True).T
+    inner = lam * np.eye(m) + Kbar.T @ Kbar
+    L_inner = scipy.linalg.cholesky(inner, lower=True)
+    return scipy.linalg.solve_triangular(L_inner, Kbar.T, lower=True)
+
+
+def lev_scores(R_desc, R_d_desc, tril_perms_lin, sig, lam, n_inducing_pts, lev_approx_idxs=None):
+    """Approximate ridge leverage scores  (solvers/iterative_solver.py:447-552).  The random subset
+    of ``max(1, n_inducing_pts // 4) * 3N`` columns is drawn with the *global* numpy RNG like the
+    reference (:471-472) unless ``lev_approx_idxs`` is given."""
+    M, D = R_desc.shape
+    dim_i = 3 * n_atoms_from_dim_d(D)
+    dim_m = np.maximum(1, n_inducing_pts // 4) * dim_i
+    if lev_approx_idxs is None:
+        lev_approx_idxs = np.sort(np.random.choice(M * dim_i, dim_m, replace=False))
+    K_nm = assemble_kernel_mat(R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=lev_approx_idxs)
+    K_mm = K_nm[lev_approx_idxs, :]
+    U = cho_factor_stable(-K_mm)
+    B = scipy.linalg.solve_triangular(U, K_nm.T, lower=False, trans='T')  # [m, n]
+    B_BT_lam = B.dot(B.T)
+    B_BT_lam[np.diag_indices_from(B_BT_lam)] += lam
+    C = cho_factor_stable(B_BT_lam)
+    C_B = scipy.linalg.solve_triangular(C, B, lower=False, trans='T')
+    scores = np.einsum('i...,i...->...', C_B, C_B)
+    return scores, np.argsort(scores)
+
+
+# --------------------------------------------------------------------------------------
+# PCG with scipy-1.7.3 legacy semantics (call site solvers/iterative_solver.py:995-1005)
+# --------------------------------------------------------------------------------------
+def pcg(matvec, b, psolve, tol, maxiter, x0=None):
+    """Preconditioned CG on ``A x = b``.  Restated from scipy 1.7.3 ``sparse.linalg.cg(tol=, atol=None)``:
+    ``atol = tol*||b||``; x0 = 0; per iteration ``z = M r; rho = r.z; p = z + (rho/rho_prev) p; q = A p;
+    alpha = rho/(p.q); x += alpha p; r -= alpha q``; stop when ``||r|| <= atol`` -- on the first hit after
+    iteration 1 the residual is recomputed as ``b - A x`` and re-tested.  The legacy driver invokes the
+    callback at the start of every iteration and once more on exit, so the reference's ``num_iters``
+    (iterative_solver.py:956) equals ``iters + 1``.
+
+    Returns (x, iters, resid, info) with info = 0 on convergence.
+    """
+    b = np.asarray(b, dtype=float)
+    x = np.zeros_like(b) if x0 is None else np.array(x0, dtype=float)
+    bnrm2 = float(np.linalg.norm(b))
+    resid = float(np.linalg.norm(matvec(x) - b))
+    if resid <= tol:
+        return x, 0, resid, 0
+    atol = tol if bnrm2 == 0 else tol * bnrm2
+    r = b - matvec(x)
+    rho_prev, p = None, None
+    it, info = 0, maxiter
+    while it < maxiter:
+        it += 1
+        z = psolve(r)
+        rho = float(np.dot(r, z))
+        p = z.copy() if it == 1 else z + (rho / rho_prev) * p
+        q = matvec(p)
+        alpha = rho / float(np.dot(p, q))
+        x = x + alpha * p
+        r = r - alpha * q
+        rho_prev = rho
+        resid = float(np.linalg.norm(r))
+        if resid <= atol and it > 1:
+            r = b - matvec(x)
+            resid = float(np.linalg.norm(r))
+        if resid <= atol:
+            info = 0
+            break
+    return x, it, resid, info
+
+
+# --------------------------------------------------------------------------------------
+# the whole solve step (solvers/iterative_solver.py:620-1108)
+# --------------------------------------------------------------------------------------
+NYSTROM_KEYS = ('lev_scores', 'random_scores', 'inverse_lev', 'lev_random', 'truncated_cholesky',
+                'truncated_cholesky_custom')
+
+
+def select_columns(str_preconditioner, R_desc, R_d_desc, tril_perms_lin, sig, lam, k, n_inducing_pts,
+                   k_truncate_task=1500):
+    """Column choice of the Nystroem variants (solvers/iterative_solver.py:683-753).  Random draws use
+    the global numpy RNG in the same order as the reference, so ``np.random.seed(s)`` before the call
+    reproduces its indices."""
+    M, D = R_desc.shape
+    n = 3 * n_atoms_from_dim_d(D) * M
+    if str_preconditioner == 'random_scores':
+        return np.sort(np.random.choice(np.arange(n), size=k, replace=False))
+    if str_preconditioner in ('truncated_cholesky', 'truncated_cholesky_custom'):
+        k_truncate = k_truncate_task if k_truncate_task < k else k
+        diag = kernel_mat_diag(R_desc, R_d_desc, tril_perms_lin, sig)
+        K_op = kernel_operator(R_desc, R_d_desc, tril_perms_lin, sig, lam)
+
+        def get_col(i):
+            e = np.zeros(n)
+            e[i] = 1
+            return -K_op(e)
+
+        k_chol = int(float(k_truncate / n) * n)  # iterative_solver.py:704 -> iterative_cholesky.py:135
+        _, index_columns = pivoted_cholesky(get_col, diag, k_chol)
+        chol_part = index_columns[:k_truncate]
+        k_random = int(k - k_truncate) if k_truncate < k else 0
+        rnd = np.random.choice(index_columns[k_truncate:], size=k_random, replace=False)
+        return np.sort(np.concatenate([chol_part, rnd]))
+    if str_preconditioner in ('lev_scores', 'inverse_lev', 'lev_random'):
+        scores, order = lev_scores(R_desc, R_d_desc, tril_perms_lin, sig, lam, n_inducing_pts)
+        if str_preconditioner == 'inverse_lev':
+            return np.sort(order[:k])
+        if str_preconditioner == 'lev_scores':
+            return np.sort(order[-k:])
+        p = scores / scores.sum()
+        return np.sort(np.random.choice(np.arange(n), size=k, replace=False, p=p))
+    raise ValueError(f'Something went wrong with str_perconditioner = {str_preconditioner}.')
+
+
+def solve(R_desc, R_d_desc, tril_perms_lin, y, sig, lam, tol, break_percentage, str_preconditioner,
+          k_truncate_task=1500, maxiter=None):
+    """``Iterative.solve`` restated: returns (alphas, num_iters, resid, inducing_pts_idxs, is_conv, extras)."""
+    M, D = R_desc.shape
+    N = n_atoms_from_dim_d(D)
+    n = 3 * N * M
+    n_inducing_pts = min(M, int(max(np.ceil(break_percentage * M), 1)))  # :652-659
+    K_op = kernel_operator(R_desc, R_d_desc, tril_perms_lin, sig, lam)
+    extras = {}
+    if str_preconditioner in NYSTROM_KEYS:
+        k = int(break_percentage * n)  # :677
+        idxs = select_columns(str_preconditioner, R_desc, R_d_desc, tril_perms_lin, sig, lam, k,
+                              n_inducing_pts, k_truncate_task)
+        assert idxs.shape == (k,), 'Incorrect number of inducing points.'
+        K_nm = assemble_kernel_mat(R_desc, R_d_desc, tril_perms_lin, sig, col_idxs=idxs)
+        if str_preconditioner == 'truncated_cholesky_custom':
+            P = nystrom_factor_sb(-K_nm, idxs, lam)
+            psolve = lambda a: -(1.0 / lam) * (a - P.T @ (P @ a))  # noqa: E731
+        else:
+            B = nystrom_factor(K_nm, idxs, lam)
+            psolve = lambda v: nystrom_apply(B, lam, v)  # noqa: E731
+            extras['B'] = B
+    elif str_preconditioner == 'cholesky':
+        diag = kernel_mat_diag(R_desc, R_d_desc, tril_perms_lin, sig)
+        k = int(break_percentage * n)  # iterative_cholesky.py:135
+
+        def get_col(i):  # iterative_cholesky.py:152-156 applied to -K_op
+            e = np.zeros(n)
+            e[i] = 1
+            return -K_op(e)
+
+        L, index_columns = pivoted_cholesky(get_col, diag, k)
+        T = woodbury_factor(L, lam)
+        psolve = lambda a: woodbury_apply(T, lam, a)  # noqa: E731
+        idxs = np.arange(int(break_percentage * n))  # :792
+        extras.update(L=L, index_columns=index_columns, T=T)
+    else:
+        raise NotImplementedError(f'str_preconditioner = {str_preconditioner}')
+    x, iters, resid, info = pcg(lambda v: -K_op(v), y, psolve, tol,
+                                3 * N * M * 5 if maxiter is None else maxiter)
+    return -x, iters + 1, resid, idxs, info == 0, extras
