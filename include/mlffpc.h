@@ -1,0 +1,165 @@
+/* libmlffpc -- C ABI of the B200-native fp64 PCG solve path for sGDML Hessian-kernel systems.
+ *
+ * The reference (bluecher31/mlff-preconditioner) is pure Python and has no FFI; this header is the
+ * boundary a maintainer binds with ctypes/cffi.  Every entry point names the
+ * reference routine it replaces (paths relative to /root/reference/src/sGDML/sgdml/).
+ *
+ * Conventions
+ *  - plain C types only; all array arguments are CALLER-OWNED DEVICE pointers (e.g. torch
+ *    tensor.data_ptr()), row-major, fp64 / int32 / int64 as stated; `stream` is a cudaStream_t
+ *    passed as void* (torch.cuda.current_stream().cuda_stream); calls are stream-ordered.
+ *  - every call returns 0 (MLFFPC_OK) or a negative status; the message is in mlffpc_last_error().
+ *    No exceptions cross the ABI.  There is no CPU fallback anywhere in this library.
+ *  - workspace sizes are queried first (*_workspace_bytes) and the caller allocates.
+ *  - notation: N atoms, D = N(N-1)/2, S permutations, M training points, dim_i = 3N, n = 3NM.
+ *    A context is sharded by training points: local rows are points [pt0, pt1), n_local = 3N(pt1-pt0).
+ */
+#ifndef MLFFPC_H
+#define MLFFPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLFFPC_OK 0
+#define MLFFPC_ERR_INVALID (-1)   /* bad argument                         -> ValueError      */
+#define MLFFPC_ERR_CUDA (-2)      /* CUDA runtime error                   -> RuntimeError    */
+#define MLFFPC_ERR_NOT_PSD (-3)   /* pivot <= 0 (incomplete_cholesky.py:62) -> AssertionError */
+#define MLFFPC_ERR_LINALG (-4)    /* Cholesky breakdown (scipy LinAlgError) -> LinAlgError   */
+#define MLFFPC_ERR_COMM (-5)      /* NCCL error                           -> RuntimeError    */
+#define MLFFPC_ERR_UNSUPPORTED (-6) /* outside the hot-path contract      -> NotImplementedError */
+
+typedef struct mlffpc_ctx mlffpc_ctx;
+
+/* ---------------------------------------------------------------- lifecycle ---- */
+int mlffpc_version(void);
+const char* mlffpc_last_error(void);
+int mlffpc_create(mlffpc_ctx** out, int device);
+int mlffpc_destroy(mlffpc_ctx* ctx);
+
+/* Multi-GPU (one process per GPU).  NCCL is bound with dlopen(libnccl_path) -- pass the libnccl.so.2
+ * that torch already loaded.  Rank 0 makes the 128-byte id, the host broadcasts it (torch.distributed),
+ * every rank calls comm_init.  The reference has no collective at all. */
+int mlffpc_comm_unique_id(const char* libnccl_path, void* id128_out);
+int mlffpc_comm_init(mlffpc_ctx* ctx, const char* libnccl_path, const void* id128, int rank, int world);
+int mlffpc_allreduce_sum(mlffpc_ctx* ctx, double* buf, int64_t count, void* stream);
+int mlffpc_allgather(mlffpc_ctx* ctx, const void* send, void* recv, int64_t bytes_per_rank, void* stream);
+
+/* ---------------------------------------------------------------- geometry ---- */
+/* Replaces the per-call re-upload of descriptors in GDMLTorchPredict.__init__ (torchtools.py:80-97)
+ * and the (R_desc, R_d_desc, tril_perms_lin) arguments every reference routine takes.
+ * R_desc[M,D], R_d_desc[M,D,3] fp64; desc_perms[S,D] int32 = pi_p(d) (tril_perms_lin de-linearised,
+ * train.py:783-790); atom_perms[S,N] int32 = task['perms'].  The input buffers must stay alive.
+ * [pt0, pt1) is this context's row block of training points (whole range for one GPU). */
+int mlffpc_geometry_workspace_bytes(int64_t M, int N, int S, int64_t* bytes);
+int mlffpc_set_geometry(mlffpc_ctx* ctx, int64_t M, int N, int S, const double* R_desc,
+                        const double* R_d_desc, const int32_t* desc_perms, const int32_t* atom_perms,
+                        double sig, int64_t pt0, int64_t pt1, void* workspace, int64_t workspace_bytes,
+                        void* stream);
+
+/* ---------------------------------------------------------------- kernel entries ---- */
+/* -diag(K) for the local rows -> out[n_local].  Replaces IterativeCholesky._assemble_kernel_mat_diag
+ * (solvers/iterative_cholesky.py:241-373). */
+int mlffpc_kernel_diag(mlffpc_ctx* ctx, double* out, void* stream);
+
+/* Explicit kernel rows: K_out[r, c] = K[row0 + r, c] for all n columns, row-major with leading
+ * dimension ld >= n.  Replaces GDMLTrain._assemble_kernel_mat(col_idxs=np.s_[:]) (train.py:1121-1308,
+ * worker :81-236). */
+int mlffpc_kernel_assemble(mlffpc_ctx* ctx, double* K_out, int64_t ld, void* stream);
+
+/* Column panel, transposed: out[c, r] = scale * K[row0 + r, cols[c]], c < b, leading dimension
+ * ld >= n_local; cols is a device int64[b] of global column indices (any order).  Replaces
+ * _assemble_kernel_mat(col_idxs=list) (train.py:1237-1263) and the one-column trick
+ * IterativeCholesky._get_col_K = K_op.matvec(e_i) (solvers/iterative_cholesky.py:152-156).
+ * Workspace: mlffpc_kernel_columns_workspace_bytes(ctx, b). */
+int mlffpc_kernel_columns_workspace_bytes(mlffpc_ctx* ctx, int64_t b, int64_t* bytes);
+int mlffpc_kernel_columns(mlffpc_ctx* ctx, const int64_t* cols, int64_t b, double* out, int64_t ld,
+                          double scale, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- operators ---- */
+/* Assembled matvec  y[r] = alpha * sum_c K[r, c] x[c] + shift * x[x_off + r]   (r < n_rows).
+ * With alpha = -1, shift = lam this is the reference's (-K_op).matvec (iterative_solver.py:416-443,
+ * :996) on an explicit K.  HBM-bound: 8*n_rows*n_cols bytes per call. */
+int mlffpc_gemv(mlffpc_ctx* ctx, const double* K, int64_t n_rows, int64_t n_cols, int64_t ld,
+                const double* x, double* y, double alpha, double shift, int64_t x_off, void* stream);
+
+/* Matrix-free matvec  y_local = alpha * (K v)_local + shift * v_local, v is the full n-vector.
+ * Replaces GDMLPredict.set_alphas + predict (predict.py:400-449, 997-1052) ->
+ * GDMLTorchPredict.set_alphas/_forward (torchtools.py:128-151, 172-272), numpy twin
+ * _predict_wkr (predict.py:72-234), and desc.d_desc_dot_vec / vec_dot_d_desc (utils/desc.py:394-428). */
+int mlffpc_matvec_free_workspace_bytes(mlffpc_ctx* ctx, int64_t* bytes);
+int mlffpc_matvec_free(mlffpc_ctx* ctx, const double* v, double* y_local, double alpha, double shift,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- dense building blocks ---- */
+/* Row-major fp64 GEMM on the FP64 tensor pipe (DMMA): C = alpha * A * op(B) + beta * C,
+ * A[m,k], op(B) = B[k,n] (trans_b = 0) or B[n,k]^T (trans_b = 1).  Stands in for the host BLAS calls
+ * L.T @ L, K_nm.T.dot(K_nm), B.dot(B.T) (iterative_cholesky.py:141, iterative_solver.py:230, :535). */
+int mlffpc_dgemm(mlffpc_ctx* ctx, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
+                 const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
+                 int64_t ldc, void* stream);
+/* W[m,m] = X X^T + shift * I  for X[m, n_cols] row-major (both triangles written; summed over ranks
+ * when a communicator is attached). */
+int mlffpc_syrk_rows(mlffpc_ctx* ctx, const double* X, int64_t m, int64_t n_cols, int64_t ldx,
+                     double shift, double* W, int64_t ldw, void* stream);
+/* In-place lower Cholesky of W[m,m] (upper triangle zeroed).  info_host: 0 ok, j > 0 = breakdown at
+ * column j.  Stands in for scipy.linalg.cholesky / cho_factor (iterative_cholesky.py:142,
+ * iterative_solver.py:580). Synchronises the stream to return info. */
+int mlffpc_potrf_lower(mlffpc_ctx* ctx, double* W, int64_t m, int64_t ldw, int* info_host, void* stream);
+/* X <- Lf^{-1} X for lower-triangular Lf[m,m] and X[m, n_cols] row-major.  Stands in for
+ * scipy.linalg.solve_triangular (iterative_cholesky.py:143, iterative_solver.py:219-226, :263-270). */
+int mlffpc_trsm_rows(mlffpc_ctx* ctx, const double* Lf, int64_t m, int64_t ldl, double* X,
+                     int64_t n_cols, int64_t ldx, void* stream);
+
+/* ---------------------------------------------------------------- pivoted partial Cholesky ---- */
+/* Greedy diagonal-pivoted partial Cholesky of A = -K (columns generated on the fly from the geometry).
+ * Replaces incomplete_cholesky.pivoted_cholesky (solvers/incomplete_cholesky.py:24-93) together with
+ * its column oracle (iterative_cholesky.py:152-156).
+ *   Lt[k, n_local] (ld >= n_local): the factor TRANSPOSED, Lt[m, r] = L[row0 + r, m]
+ *   diag[n_local]: in = -diag(K) local rows, out = residual diagonal
+ *   index_columns[n] int64 (replicated, out): the reference's permutation, first k = pivot sequence
+ *   forced_pivots: NULL, or device int64[k] to replay a pivot sequence (tie diagnostics)
+ *   step_ms_host: NULL, or host float[k] receiving per-step times (info['time_cholesky'])
+ * Returns MLFFPC_ERR_NOT_PSD when a pivot is <= 0. */
+int mlffpc_pchol_workspace_bytes(mlffpc_ctx* ctx, int64_t k, int64_t* bytes);
+int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, double* diag,
+                       int64_t* index_columns, const int64_t* forced_pivots, float* step_ms_host,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- preconditioner ---- */
+/* Woodbury factor, in place: T = chol_lower(lam I_k + Lt Lt^T)^{-1} Lt   [k, n_local].
+ * Replaces iterative_cholesky.py:141-143.  W is a k*k device scratch. */
+int mlffpc_woodbury_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, double lam, double* W,
+                           void* stream);
+/* z = sign * (r - T^T (T r)) / lam  on the local rows; u is a k-vector device scratch.
+ * sign = +1: iterative_cholesky.py:145-148; sign = -1: the Nystroem operator
+ * (iterative_solver.py:315-318) and _init_precon_operator_sb (:376-379). */
+int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
+                        const double* r, double* z, double* u, void* stream);
+
+/* ---------------------------------------------------------------- PCG ---- */
+/* Preconditioned CG on A x = b, A = -K + lam I, with scipy-1.7.3 legacy stopping semantics
+ * (||r|| <= tol ||b||, residual recomputed once on first hit; call site iterative_solver.py:995-1005).
+ *   K_local: explicit local rows [n_local, n] (ld_k) or NULL for the matrix-free operator
+ *   T: preconditioner factor [k, n_local] or NULL (identity); precon_sign as in mlffpc_precon_apply
+ *   b, x: local rows (x in: initial guess, out: solution)
+ *   out_host[4] (host doubles): iterations, final ||r||, info (0 converged), ||b||
+ *   resid_hist_host: NULL or host double[maxiter+1] receiving ||r|| per iteration
+ * Workspace: mlffpc_pcg_workspace_bytes. */
+int mlffpc_pcg_workspace_bytes(mlffpc_ctx* ctx, int64_t k, int matrix_free, int64_t* bytes);
+int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam, const double* T,
+               int64_t k, int64_t ld_t, double precon_sign, const double* b, double* x, double tol,
+               int64_t maxiter, double* out_host, double* resid_hist_host, void* workspace,
+               int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- small vector helpers ---- */
+/* out[i] = X[rows[i], :] gathered rows etc. are done with torch indexing on the host side; the only
+ * vector helpers exported are the fused CG kernels, for tests:                                   */
+int mlffpc_dot(mlffpc_ctx* ctx, const double* a, const double* b, int64_t n, double* out_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLFFPC_H */

@@ -1,0 +1,139 @@
+// Shared declarations for libmlffpc (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/mlffpc.h"
+
+namespace mlffpc {
+
+// ---- error plumbing: every extern "C" entry returns a status, message via mlffpc_last_error() ----
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define MLFFPC_CUDA(call)                                                          \
+    do {                                                                           \
+        cudaError_t _e = (call);                                                   \
+        if (_e != cudaSuccess) return mlffpc::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define MLFFPC_LAUNCH_CHECK()                                                      \
+    do {                                                                           \
+        cudaError_t _e = cudaGetLastError();                                       \
+        if (_e != cudaSuccess) return mlffpc::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define MLFFPC_REQUIRE(cond, ...)                                                  \
+    do {                                                                           \
+        if (!(cond)) {                                                             \
+            mlffpc::set_error(__VA_ARGS__);                                        \
+            return MLFFPC_ERR_INVALID;                                             \
+        }                                                                          \
+    } while (0)
+
+#define MLFFPC_TRY(call)                                                           \
+    do {                                                                           \
+        int _s = (call);                                                           \
+        if (_s != MLFFPC_OK) return _s;                                            \
+    } while (0)
+
+// ---- NCCL, bound at run time with dlopen (comm.cu) ----
+struct Comm {
+    void* lib = nullptr;
+    void* comm = nullptr;  // ncclComm_t
+    int rank = 0;
+    int world = 1;
+};
+int comm_allreduce_sum(Comm& c, double* buf, size_t count, cudaStream_t s);
+int comm_allgather(Comm& c, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s);
+int comm_broadcast(Comm& c, void* buf, size_t bytes, int root, cudaStream_t s);
+
+}  // namespace mlffpc
+
+// The opaque context.  Holds no large allocations: geometry tables live in caller-owned workspace.
+struct mlffpc_ctx {
+    int device = 0;
+    int num_sms = 148;
+    // geometry (device pointers into caller buffers / workspace)
+    int64_t M = 0;
+    int N = 0, S = 0, D = 0, dim_i = 0;
+    int64_t n = 0;
+    double sig = 0.0;
+    const double* R_desc = nullptr;    // [M, D]
+    const double* R_d_desc = nullptr;  // [M, D, 3]
+    const int32_t* desc_perms = nullptr;  // [S, D]  pi_p(d)
+    const int32_t* atom_perms = nullptr;  // [S, N]  P_p
+    int32_t* atom_perms_inv = nullptr;    // [S, N]  (workspace)
+    int32_t* pair_a = nullptr;            // [D] larger atom index   (workspace)
+    int32_t* pair_b = nullptr;            // [D] smaller atom index  (workspace)
+    double* Xp = nullptr;                 // [M*S, D] permuted descriptors (workspace; == R_desc if S == 1)
+    // row-block shard: local rows are points [pt0, pt1)
+    int64_t pt0 = 0, pt1 = 0;
+    int64_t n_local() const { return (pt1 - pt0) * (int64_t)dim_i; }
+    int64_t row0() const { return pt0 * (int64_t)dim_i; }
+    mlffpc::Comm comm;
+    // small persistent device scratch owned by the ctx (scalars / partial reductions, a few KB)
+    double* scal = nullptr;    // device scalars
+    double* h_scal = nullptr;  // pinned host mirror
+    double* partials = nullptr;  // [MLFFPC_MAX_PARTIALS * 4]
+};
+
+#define MLFFPC_MAX_PARTIALS 65536
+#define MLFFPC_NUM_SCAL 64
+
+namespace mlffpc {
+
+// ---- device helpers ----
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum, result valid in every thread; sm must hold >= 33 doubles
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = (lane < nw) ? sm[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) sm[32] = t;
+    }
+    __syncthreads();
+    return sm[32];
+}
+
+// index of pair (x, y), x != y, in np.tril_indices(N, -1) order: a(a-1)/2 + b with a > b
+__device__ __forceinline__ int pair_index(int x, int y) {
+    const int a = x > y ? x : y, b = x > y ? y : x;
+    return a * (a - 1) / 2 + b;
+}
+
+// HBM-bound matrix-vector kernels (gemv.cu)
+int launch_gemv_rows(const double* K, int64_t n_rows, int64_t n_cols, int64_t ld, const double* x,
+                     double* y, double alpha, double shift, int64_t x_off, cudaStream_t s);
+int launch_tgemv_cols(const double* T, int64_t k, int64_t n_cols, int64_t ld, const double* w,
+                      double* out, int post, const double* r, double sign_over_lam, int num_sms,
+                      cudaStream_t s);
+// one column of scale*K on the local rows, column index read from device memory (geometry.cu)
+int launch_columns_device_col(mlffpc_ctx* ctx, const int64_t* col_dev, double* out, double scale,
+                              cudaStream_t s);
+// matrix-free operator (matvec.cu)
+int64_t matvec_free_ws_bytes(const mlffpc_ctx* ctx);
+int matvec_free(mlffpc_ctx* ctx, const double* v, double* y_local, double alpha, double shift,
+                void* workspace, cudaStream_t s);
+// preconditioner apply (precon.cu)
+int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
+                 const double* r, double* z, double* u, cudaStream_t s);
+
+// internal dense building blocks (dense.cu), all on `s`
+int dgemm(bool transB, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only,
+          cudaStream_t s);
+
+}  // namespace mlffpc

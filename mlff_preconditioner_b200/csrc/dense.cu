@@ -1,0 +1,371 @@
+// fp64 dense building blocks on the DMMA pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has
+// no fp64 kind on sm_100): row-major GEMM, SYRK over long rows, blocked Cholesky, blocked row-TRSM.
+#include "common.cuh"
+
+namespace mlffpc {
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool pred) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gsrc), "r"(sz));
+}
+// 16-byte copy of which only the first `src_bytes` (0, 8 or 16) are read; the rest is zero-filled
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ int vec2_bytes(bool row_ok, int64_t idx, int64_t lim) {
+    if (!row_ok || idx >= lim) return 0;
+    return (idx + 1 < lim) ? 16 : 8;
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+// C[m,n] = alpha * A[m,k] * op(B) + beta * C.   BK = 16, 3-stage cp.async pipeline, 256 threads.
+// smem strides are == 4 (mod 16) doubles so the m8n8k4 fragment loads are bank-conflict free.
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_THREADS = 256;
+
+template <int BM, int BN, bool TRANSB>
+struct GemmSmem {
+    static constexpr int A_STRIDE = GEMM_BK + 4;                  // As[BM][A_STRIDE]
+    static constexpr int B_STRIDE = TRANSB ? (GEMM_BK + 4) : (BN + 4);  // Bs[BN][..] or Bs[BK][..]
+    static constexpr int A_ELEMS = BM * A_STRIDE;
+    static constexpr int B_ELEMS = TRANSB ? BN * B_STRIDE : GEMM_BK * B_STRIDE;
+    static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    static constexpr size_t BYTES = (size_t)GEMM_STAGES * STAGE_ELEMS * sizeof(double);
+};
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool TRANSB, bool VEC2>
+__global__ void __launch_bounds__(GEMM_THREADS)
+dgemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __restrict__ A, int64_t lda,
+             const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C, int64_t ldc,
+             int lower_only) {
+    using SM = GemmSmem<BM, BN, TRANSB>;
+    constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;  // warp tile
+    constexpr int TM = WM / 8, TN = WN / 8;              // 8x8 mma tiles per warp
+    static_assert(WARPS_M * WARPS_N * 32 == GEMM_THREADS, "8 warps");
+    extern __shared__ double smem[];
+
+    const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+    if (lower_only && n0 > m0 + BM - 1) return;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp / WARPS_N) * WM, wn = (warp % WARPS_N) * WN;
+    const int lr = lane >> 2, lc = lane & 3;
+
+    double acc[TM][TN][2];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int64_t ktiles = (k + GEMM_BK - 1) / GEMM_BK;
+
+    auto load_stage = [&](int stage, int64_t kt) {
+        double* As = smem + (size_t)stage * SM::STAGE_ELEMS;
+        double* Bs = As + SM::A_ELEMS;
+        const int64_t k0 = kt * GEMM_BK;
+        constexpr int V = VEC2 ? 2 : 1;
+        // A tile: BM x BK, k contiguous
+        constexpr int A_ITEMS = BM * GEMM_BK / V;
+        for (int t = tid; t < A_ITEMS; t += GEMM_THREADS) {
+            const int r = t / (GEMM_BK / V), c = (t % (GEMM_BK / V)) * V;
+            const bool ok = (m0 + r < m) && (k0 + c < k);
+            const double* src = ok ? (A + (m0 + r) * lda + k0 + c) : A;
+            if (VEC2) cp_async16(As + r * SM::A_STRIDE + c, src, vec2_bytes(m0 + r < m, k0 + c, k));
+            else cp_async8(As + r * SM::A_STRIDE + c, src, ok);
+        }
+        if (TRANSB) {  // B[n, k], k contiguous -> Bs[BN][BK+4]
+            constexpr int B_ITEMS = BN * GEMM_BK / V;
+            for (int t = tid; t < B_ITEMS; t += GEMM_THREADS) {
+                const int r = t / (GEMM_BK / V), c = (t % (GEMM_BK / V)) * V;
+                const bool ok = (n0 + r < n) && (k0 + c < k);
+                const double* src = ok ? (B + (n0 + r) * ldb + k0 + c) : B;
+                if (VEC2) cp_async16(Bs + r * SM::B_STRIDE + c, src, vec2_bytes(n0 + r < n, k0 + c, k));
+                else cp_async8(Bs + r * SM::B_STRIDE + c, src, ok);
+            }
+        } else {  // B[k, n], n contiguous -> Bs[BK][BN+4]
+            constexpr int B_ITEMS = GEMM_BK * BN / V;
+            for (int t = tid; t < B_ITEMS; t += GEMM_THREADS) {
+                const int r = t / (BN / V), c = (t % (BN / V)) * V;
+                const bool ok = (k0 + r < k) && (n0 + c < n);
+                const double* src = ok ? (B + (k0 + r) * ldb + n0 + c) : B;
+                if (VEC2) cp_async16(Bs + r * SM::B_STRIDE + c, src, vec2_bytes(k0 + r < k, n0 + c, n));
+                else cp_async8(Bs + r * SM::B_STRIDE + c, src, ok);
+            }
+        }
+    };
+
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+        if (s < ktiles) load_stage(s, s);
+        cp_async_commit();
+    }
+
+    for (int64_t kt = 0; kt < ktiles; ++kt) {
+        cp_async_wait<GEMM_STAGES - 2>();
+        __syncthreads();
+        {
+            const int64_t nk = kt + GEMM_STAGES - 1;
+            if (nk < ktiles) load_stage((int)(nk % GEMM_STAGES), nk);
+            cp_async_commit();
+        }
+        const double* As = smem + (size_t)(kt % GEMM_STAGES) * SM::STAGE_ELEMS;
+        const double* Bs = As + SM::A_ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < GEMM_BK; kk += 4) {
+            double af[TM], bf[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) af[i] = As[(wm + i * 8 + lr) * SM::A_STRIDE + kk + lc];
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+                bf[j] = TRANSB ? Bs[(wn + j * 8 + lr) * SM::B_STRIDE + kk + lc]
+                               : Bs[(kk + lc) * SM::B_STRIDE + wn + j * 8 + lr];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int64_t row = m0 + wm + i * 8 + lr;
+        if (row >= m) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int64_t col = n0 + wn + j * 8 + 2 * lc;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (col + e < n) {
+                    double* p = C + row * ldc + col + e;
+                    const double v = alpha * acc[i][j][e];
+                    *p = (beta == 0.0) ? v : fma(beta, *p, v);
+                }
+            }
+        }
+    }
+}
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool TRANSB, bool VEC2>
+static int launch_dgemm(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                        const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+                        bool lower_only, cudaStream_t s) {
+    using SM = GemmSmem<BM, BN, TRANSB>;
+    auto kern = dgemm_kernel<BM, BN, WARPS_M, WARPS_N, TRANSB, VEC2>;
+    MLFFPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES));
+    dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
+    MLFFPC_REQUIRE(grid.y <= 65535, "dgemm: m = %lld too large for this launch shape", (long long)m);
+    kern<<<grid, GEMM_THREADS, SM::BYTES, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0);
+    MLFFPC_LAUNCH_CHECK();
+    return MLFFPC_OK;
+}
+
+int dgemm(bool transB, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only,
+          cudaStream_t s) {
+    if (m <= 0 || n <= 0) return MLFFPC_OK;
+    const bool vec2 = (lda % 2 == 0) && (ldb % 2 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
+    const bool narrow = (n <= 64);
+#define MLFFPC_GEMM_DISPATCH(TB, V2)                                                                      \
+    (narrow ? launch_dgemm<128, 64, 4, 2, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s) \
+            : launch_dgemm<128, 128, 2, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s))
+    if (transB) return vec2 ? MLFFPC_GEMM_DISPATCH(true, true) : MLFFPC_GEMM_DISPATCH(true, false);
+    return vec2 ? MLFFPC_GEMM_DISPATCH(false, true) : MLFFPC_GEMM_DISPATCH(false, false);
+#undef MLFFPC_GEMM_DISPATCH
+}
+
+// ---- SYRK helpers ---------------------------------------------------------------------------
+__global__ void symmetrize_shift_kernel(double* W, int64_t m, int64_t ldw, double shift) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = blockIdx.y;
+    if (c >= m) return;
+    if (c > r) W[r * ldw + c] = W[c * ldw + r];
+    else if (c == r) W[r * ldw + c] += shift;
+}
+
+// ---- blocked Cholesky (lower, in place) --------------------------------------------------------
+constexpr int POTRF_NB = 64;
+
+// factor the nb x nb diagonal block at (j0, j0) in shared memory; writes info (1-based column) on breakdown
+__global__ void potrf_diag_kernel(double* W, int64_t ldw, int64_t j0, int nb, int* info) {
+    __shared__ double a[POTRF_NB][POTRF_NB + 1];
+    const int tid = threadIdx.x;
+    for (int t = tid; t < nb * nb; t += blockDim.x) a[t / nb][t % nb] = W[(j0 + t / nb) * ldw + j0 + t % nb];
+    __syncthreads();
+    for (int j = 0; j < nb; ++j) {
+        __shared__ double piv;
+        if (tid == 0) {
+            const double d = a[j][j];
+            if (!(d > 0.0)) {
+                if (*info == 0) *info = (int)(j0 + j + 1);
+                piv = 1.0;  // keep going with garbage; caller reads info
+            } else {
+                piv = sqrt(d);
+            }
+            a[j][j] = piv;
+        }
+        __syncthreads();
+        const double pj = a[j][j];
+        for (int r = j + 1 + tid; r < nb; r += blockDim.x) a[r][j] /= pj;
+        __syncthreads();
+        // trailing update of the block: a[r][c] -= a[r][j] a[c][j], c in (j, r]
+        for (int t = tid; t < (nb - j - 1) * (nb - j - 1); t += blockDim.x) {
+            const int r = j + 1 + t / (nb - j - 1), c = j + 1 + t % (nb - j - 1);
+            if (c <= r) a[r][c] -= a[r][j] * a[c][j];
+        }
+        __syncthreads();
+    }
+    for (int t = tid; t < nb * nb; t += blockDim.x) {
+        const int r = t / nb, c = t % nb;
+        W[(j0 + r) * ldw + j0 + c] = (c <= r) ? a[r][c] : 0.0;
+    }
+}
+
+// panel below the diagonal block: rows r in [j0+nb, m): W[r, j0:j0+nb] <- W[r, j0:j0+nb] L11^{-T}; one thread per row
+__global__ void potrf_panel_kernel(double* W, int64_t ldw, int64_t j0, int nb, int64_t m) {
+    __shared__ double l11[POTRF_NB][POTRF_NB + 1];
+    for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) l11[t / nb][t % nb] = W[(j0 + t / nb) * ldw + j0 + t % nb];
+    __syncthreads();
+    const int64_t r = j0 + nb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    double x[POTRF_NB];
+    double* row = W + r * ldw + j0;
+#pragma unroll 4
+    for (int c = 0; c < nb; ++c) x[c] = row[c];
+    for (int c = 0; c < nb; ++c) {
+        double v = x[c];
+        for (int t = 0; t < c; ++t) v = fma(-x[t], l11[c][t], v);
+        x[c] = v / l11[c][c];
+    }
+    for (int c = 0; c < nb; ++c) row[c] = x[c];
+}
+
+__global__ void zero_upper_kernel(double* W, int64_t m, int64_t ldw) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = blockIdx.y;
+    if (c < m && c > r) W[r * ldw + c] = 0.0;
+}
+
+// ---- blocked row-TRSM: X <- Lf^{-1} X, X[m, n_cols] row-major ------------------------------------
+constexpr int TRSM_NB = 32;
+
+// diagonal solve for block rows [j0, j0+nb): one thread per column of X
+__global__ void trsm_diag_kernel(const double* __restrict__ Lf, int64_t ldl, int64_t j0, int nb, double* X,
+                                 int64_t n_cols, int64_t ldx) {
+    __shared__ double l[TRSM_NB][TRSM_NB + 1];
+    for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) l[t / nb][t % nb] = Lf[(j0 + t / nb) * ldl + j0 + t % nb];
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    double x[TRSM_NB];
+#pragma unroll
+    for (int r = 0; r < TRSM_NB; ++r)
+        if (r < nb) x[r] = X[(j0 + r) * ldx + c];
+#pragma unroll
+    for (int r = 0; r < TRSM_NB; ++r) {
+        if (r < nb) {
+            double v = x[r];
+#pragma unroll
+            for (int t = 0; t < TRSM_NB; ++t)
+                if (t < r) v = fma(-l[r][t], x[t], v);
+            x[r] = v / l[r][r];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < TRSM_NB; ++r)
+        if (r < nb) X[(j0 + r) * ldx + c] = x[r];
+}
+
+}  // namespace mlffpc
+
+using namespace mlffpc;
+
+extern "C" {
+
+int mlffpc_dgemm(mlffpc_ctx* ctx, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
+                 const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
+                 int64_t ldc, void* stream) {
+    MLFFPC_REQUIRE(ctx && A && B && C, "dgemm: NULL argument");
+    MLFFPC_REQUIRE(m >= 0 && n >= 0 && k >= 0 && lda >= k && ldc >= n && ldb >= (trans_b ? k : n),
+                   "dgemm: bad dimensions");
+    return dgemm(trans_b != 0, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, false, (cudaStream_t)stream);
+}
+
+int mlffpc_syrk_rows(mlffpc_ctx* ctx, const double* X, int64_t m, int64_t n_cols, int64_t ldx,
+                     double shift, double* W, int64_t ldw, void* stream) {
+    MLFFPC_REQUIRE(ctx && X && W && m > 0 && n_cols >= 0 && ldx >= n_cols && ldw >= m, "syrk_rows: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    MLFFPC_TRY(dgemm(true, m, m, n_cols, 1.0, X, ldx, X, ldx, 0.0, W, ldw, true, s));
+    if (ctx->comm.world > 1) {
+        // the lower tiles of every rank are summed; entries above the diagonal tiles are rebuilt below
+        MLFFPC_REQUIRE(ldw == m, "syrk_rows: multi-GPU reduction needs a packed W (ldw == m)");
+        symmetrize_shift_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)m), 256, 0, s>>>(W, m, ldw, 0.0);
+        MLFFPC_LAUNCH_CHECK();
+        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, W, (size_t)(m * m), s));
+    }
+    symmetrize_shift_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)m), 256, 0, s>>>(W, m, ldw, shift);
+    MLFFPC_LAUNCH_CHECK();
+    return MLFFPC_OK;
+}
+
+int mlffpc_potrf_lower(mlffpc_ctx* ctx, double* W, int64_t m, int64_t ldw, int* info_host, void* stream) {
+    MLFFPC_REQUIRE(ctx && W && info_host && m > 0 && ldw >= m, "potrf_lower: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    int* d_info = (int*)(ctx->scal + MLFFPC_NUM_SCAL - 2);
+    MLFFPC_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), s));
+    for (int64_t j0 = 0; j0 < m; j0 += POTRF_NB) {
+        const int nb = (int)((m - j0 < POTRF_NB) ? (m - j0) : POTRF_NB);
+        potrf_diag_kernel<<<1, 256, 0, s>>>(W, ldw, j0, nb, d_info);
+        MLFFPC_LAUNCH_CHECK();
+        const int64_t rest = m - j0 - nb;
+        if (rest > 0) {
+            potrf_panel_kernel<<<(unsigned)((rest + 127) / 128), 128, 0, s>>>(W, ldw, j0, nb, m);
+            MLFFPC_LAUNCH_CHECK();
+            // A22 -= L21 L21^T (lower tiles only)
+            double* A22 = W + (j0 + nb) * ldw + (j0 + nb);
+            const double* L21 = W + (j0 + nb) * ldw + j0;
+            MLFFPC_TRY(dgemm(true, rest, rest, nb, -1.0, L21, ldw, L21, ldw, 1.0, A22, ldw, true, s));
+        }
+    }
+    zero_upper_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)m), 256, 0, s>>>(W, m, ldw);
+    MLFFPC_LAUNCH_CHECK();
+    int* h_info = (int*)(ctx->h_scal + MLFFPC_NUM_SCAL - 2);
+    MLFFPC_CUDA(cudaMemcpyAsync(h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MLFFPC_CUDA(cudaStreamSynchronize(s));
+    *info_host = *h_info;
+    return MLFFPC_OK;
+}
+
+int mlffpc_trsm_rows(mlffpc_ctx* ctx, const double* Lf, int64_t m, int64_t ldl, double* X,
+                     int64_t n_cols, int64_t ldx, void* stream) {
+    MLFFPC_REQUIRE(ctx && Lf && X && m > 0 && ldl >= m && n_cols >= 0 && ldx >= n_cols, "trsm_rows: bad argument");
+    if (n_cols == 0) return MLFFPC_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int64_t j0 = 0; j0 < m; j0 += TRSM_NB) {
+        const int nb = (int)((m - j0 < TRSM_NB) ? (m - j0) : TRSM_NB);
+        trsm_diag_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, s>>>(Lf, ldl, j0, nb, X, n_cols, ldx);
+        MLFFPC_LAUNCH_CHECK();
+        const int64_t rest = m - j0 - nb;
+        if (rest > 0) {
+            // X[j0+nb:, :] -= Lf[j0+nb:, j0:j0+nb] X[j0:j0+nb, :]
+            MLFFPC_TRY(dgemm(false, rest, n_cols, nb, -1.0, Lf + (j0 + nb) * ldl + j0, ldl, X + j0 * ldx, ldx,
+                             1.0, X + (j0 + nb) * ldx, ldx, false, s));
+        }
+    }
+    return MLFFPC_OK;
+}
+
+}  // extern "C"

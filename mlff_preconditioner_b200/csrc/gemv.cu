@@ -1,0 +1,162 @@
+// HBM-bound fp64 matrix-vector kernels over row-major matrices.
+//  * gemv_rows:  y = alpha * K x + shift * x_local     (K streamed once, 8*rows*cols bytes)
+//  * tgemv_cols: out[c] = sum_m T[m, c] w[m]            (column combination, coalesced across c)
+#include "common.cuh"
+
+namespace mlffpc {
+
+constexpr int GEMV_ROWS = 8;      // rows per CTA: x is re-read from L2 once per 8 rows of K
+constexpr int GEMV_THREADS = 256;
+
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+    // streaming (evict-first) 128-bit load: K is touched exactly once per matvec
+    return __ldcs(reinterpret_cast<const double2*>(p));
+}
+
+template <bool VEC2>
+__global__ void __launch_bounds__(GEMV_THREADS)
+gemv_rows_kernel(const double* __restrict__ K, int64_t n_rows, int64_t n_cols, int64_t ld,
+                 const double* __restrict__ x, double* __restrict__ y, double alpha, double shift,
+                 int64_t x_off) {
+    __shared__ double red[GEMV_ROWS][GEMV_THREADS / 32];
+    const int64_t r0 = (int64_t)blockIdx.x * GEMV_ROWS;
+    const int tid = threadIdx.x;
+    double acc[GEMV_ROWS];
+#pragma unroll
+    for (int r = 0; r < GEMV_ROWS; ++r) acc[r] = 0.0;
+
+    const double* rowp[GEMV_ROWS];
+#pragma unroll
+    for (int r = 0; r < GEMV_ROWS; ++r) {
+        const int64_t rr = (r0 + r < n_rows) ? (r0 + r) : (n_rows - 1);  // clamp: tail rows recompute the last row
+        rowp[r] = K + rr * ld;
+    }
+
+    if (VEC2) {
+        const int64_t nv = n_cols >> 1;
+        for (int64_t c = tid; c < nv; c += GEMV_THREADS) {
+            const double2 xv = __ldg(reinterpret_cast<const double2*>(x) + c);
+            double2 kv[GEMV_ROWS];
+#pragma unroll
+            for (int r = 0; r < GEMV_ROWS; ++r) kv[r] = ld_stream2(rowp[r] + 2 * c);
+#pragma unroll
+            for (int r = 0; r < GEMV_ROWS; ++r) acc[r] = fma(kv[r].y, xv.y, fma(kv[r].x, xv.x, acc[r]));
+        }
+        if ((n_cols & 1) && tid == 0) {
+            const double xs = x[n_cols - 1];
+#pragma unroll
+            for (int r = 0; r < GEMV_ROWS; ++r) acc[r] = fma(rowp[r][n_cols - 1], xs, acc[r]);
+        }
+    } else {
+        for (int64_t c = tid; c < n_cols; c += GEMV_THREADS) {
+            const double xs = __ldg(x + c);
+#pragma unroll
+            for (int r = 0; r < GEMV_ROWS; ++r) acc[r] = fma(__ldcs(rowp[r] + c), xs, acc[r]);
+        }
+    }
+
+    const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+    for (int r = 0; r < GEMV_ROWS; ++r) {
+        const double v = warp_sum(acc[r]);
+        if (lane == 0) red[r][w] = v;
+    }
+    __syncthreads();
+    if (tid < GEMV_ROWS) {
+        const int64_t row = r0 + tid;
+        if (row < n_rows) {
+            double v = 0.0;
+#pragma unroll
+            for (int i = 0; i < GEMV_THREADS / 32; ++i) v += red[tid][i];
+            v *= alpha;
+            if (shift != 0.0) v = fma(shift, x[x_off + row], v);
+            y[row] = v;
+        }
+    }
+}
+
+// out[c] = post( sum_{m < k} T[m*ld + c] * w[m] ) ; threads over columns, MSPLIT slices of m per CTA.
+// POST: 0 = plain store; 1 = precon apply: out = sign*(r - acc)/lam.
+constexpr int TGEMV_THREADS = 256;
+
+template <int MSPLIT>
+__global__ void __launch_bounds__(TGEMV_THREADS)
+tgemv_cols_kernel(const double* __restrict__ T, int64_t k, int64_t n_cols, int64_t ld,
+                  const double* __restrict__ w, double* __restrict__ out, int post,
+                  const double* __restrict__ r, double sign_over_lam) {
+    constexpr int COLS = TGEMV_THREADS / MSPLIT;
+    __shared__ double red[MSPLIT][COLS];
+    const int tc = threadIdx.x % COLS, ts = threadIdx.x / COLS;
+    const int64_t c = (int64_t)blockIdx.x * COLS + tc;
+    double acc = 0.0;
+    if (c < n_cols) {
+        const double* Tp = T + c;
+        int64_t m = ts;
+        // 8 independent loads in flight per thread
+        for (; m + 7 * MSPLIT < k; m += 8 * MSPLIT) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldcs(Tp + (m + u * MSPLIT) * ld);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = fma(t[u], __ldg(w + m + u * MSPLIT), acc);
+        }
+        for (; m < k; m += MSPLIT) acc = fma(__ldcs(Tp + m * ld), __ldg(w + m), acc);
+    }
+    if (MSPLIT > 1) {
+        red[ts][tc] = acc;
+        __syncthreads();
+        if (ts != 0) return;
+#pragma unroll
+        for (int s = 1; s < MSPLIT; ++s) acc += red[s][tc];
+    }
+    if (c < n_cols) {
+        if (post == 1) acc = sign_over_lam * (r[c] - acc);
+        out[c] = acc;
+    }
+}
+
+int launch_gemv_rows(const double* K, int64_t n_rows, int64_t n_cols, int64_t ld, const double* x,
+                     double* y, double alpha, double shift, int64_t x_off, cudaStream_t s) {
+    if (n_rows <= 0) return MLFFPC_OK;
+    const unsigned grid = (unsigned)((n_rows + GEMV_ROWS - 1) / GEMV_ROWS);
+    const bool vec2 = (ld % 2 == 0) && (((uintptr_t)K | (uintptr_t)x) % 16 == 0);
+    if (vec2)
+        gemv_rows_kernel<true><<<grid, GEMV_THREADS, 0, s>>>(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off);
+    else
+        gemv_rows_kernel<false><<<grid, GEMV_THREADS, 0, s>>>(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off);
+    MLFFPC_LAUNCH_CHECK();
+    return MLFFPC_OK;
+}
+
+int launch_tgemv_cols(const double* T, int64_t k, int64_t n_cols, int64_t ld, const double* w,
+                      double* out, int post, const double* r, double sign_over_lam, int num_sms,
+                      cudaStream_t s) {
+    if (n_cols <= 0) return MLFFPC_OK;
+    // enough threads to keep HBM busy: aim for >= 2 full waves of 256-thread CTAs
+    const int64_t want = (int64_t)num_sms * 2048;
+    if (n_cols >= want || k < 64) {
+        tgemv_cols_kernel<1><<<(unsigned)((n_cols + 255) / 256), TGEMV_THREADS, 0, s>>>(T, k, n_cols, ld, w, out, post, r, sign_over_lam);
+    } else if (n_cols * 4 >= want || k < 256) {
+        tgemv_cols_kernel<4><<<(unsigned)((n_cols + 63) / 64), TGEMV_THREADS, 0, s>>>(T, k, n_cols, ld, w, out, post, r, sign_over_lam);
+    } else {
+        tgemv_cols_kernel<8><<<(unsigned)((n_cols + 31) / 32), TGEMV_THREADS, 0, s>>>(T, k, n_cols, ld, w, out, post, r, sign_over_lam);
+    }
+    MLFFPC_LAUNCH_CHECK();
+    return MLFFPC_OK;
+}
+
+}  // namespace mlffpc
+
+using namespace mlffpc;
+
+extern "C" {
+
+int mlffpc_gemv(mlffpc_ctx* ctx, const double* K, int64_t n_rows, int64_t n_cols, int64_t ld,
+                const double* x, double* y, double alpha, double shift, int64_t x_off, void* stream) {
+    MLFFPC_REQUIRE(ctx && K && x && y, "gemv: NULL argument");
+    MLFFPC_REQUIRE(n_rows >= 0 && n_cols > 0 && ld >= n_cols && x_off >= 0, "gemv: bad dimensions");
+    MLFFPC_REQUIRE(shift == 0.0 || x_off + n_rows <= n_cols, "gemv: shift term indexes x out of range");
+    return launch_gemv_rows(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,274 @@
+// Preconditioned CG driver with device-resident scalars and fused vector kernels.
+// Recurrence and stopping rule restate scipy 1.7.3 sparse.linalg.cg(tol=, atol=None) as called by the
+// reference (solvers/iterative_solver.py:995-1005): atol = tol*||b||, probe ||A x0 - b|| <= tol first,
+// on the first ||r|| <= atol after iteration 1 recompute r = b - A x once and re-test.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mlffpc {
+
+constexpr int VEC_THREADS = 256;
+constexpr int VEC_MAX_BLOCKS = 1024;
+
+// scalar slots in ctx->scal
+enum { S_RHO0 = 0, S_RHO1 = 1, S_PQ = 2, S_RR = 3, S_TMP = 4, S_COUNTER = 8 /* unsigned */ };
+
+// deterministic grid reduction: per-block partials, the last block to finish sums them in index order
+__device__ __forceinline__ void grid_reduce_store(double v, double* partials, unsigned* counter, double* out) {
+    __shared__ double sm[40];
+    __shared__ bool is_last;
+    v = block_sum(v, sm);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = v;
+        __threadfence();
+        const unsigned done = atomicAdd(counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double t = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += ((volatile double*)partials)[i];
+        t = block_sum(t, sm);
+        if (threadIdx.x == 0) {
+            *out = t;
+            *counter = 0u;
+        }
+    }
+}
+
+__global__ void dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
+                           double* partials, unsigned* counter, double* out) {
+    double v = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        v = fma(a[i], b[i], v);
+    grid_reduce_store(v, partials, counter, out);
+}
+
+// p = z + (rho/rho_prev) p   (first = 1: p = z)
+__global__ void update_p_kernel(const double* __restrict__ z, double* __restrict__ p, int64_t n,
+                                const double* __restrict__ rho, const double* __restrict__ rho_prev, int first) {
+    const double beta = first ? 0.0 : (*rho / *rho_prev);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = first ? z[i] : fma(beta, p[i], z[i]);
+}
+
+// alpha = rho/pq; x += alpha p; r -= alpha q; rr = sum r^2
+__global__ void update_xr_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                                 const double* __restrict__ q, int64_t n, const double* __restrict__ rho,
+                                 const double* __restrict__ pq, double* partials, unsigned* counter, double* rr) {
+    const double alpha = *rho / *pq;
+    double v = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double ri = fma(-alpha, q[i], r[i]);
+        r[i] = ri;
+        v = fma(ri, ri, v);
+    }
+    grid_reduce_store(v, partials, counter, rr);
+}
+
+// r = b - q ; rr = sum r^2
+__global__ void residual_kernel(const double* __restrict__ b, const double* __restrict__ q, double* __restrict__ r,
+                                int64_t n, double* partials, unsigned* counter, double* rr) {
+    double v = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = b[i] - q[i];
+        r[i] = ri;
+        v = fma(ri, ri, v);
+    }
+    grid_reduce_store(v, partials, counter, rr);
+}
+
+static inline unsigned vec_grid(int64_t n) {
+    int64_t g = (n + VEC_THREADS - 1) / VEC_THREADS;
+    if (g > VEC_MAX_BLOCKS) g = VEC_MAX_BLOCKS;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+struct PcgWs {
+    int64_t n_pad, off_r, off_z, off_q, off_p, off_xg, off_u, off_mv, total;
+};
+static PcgWs pcg_layout(const mlffpc_ctx* c, int64_t k, bool matrix_free) {
+    auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+    PcgWs w;
+    const int world = c->comm.world;
+    const int64_t ppr = (c->M + world - 1) / world;
+    w.n_pad = ppr * c->dim_i;
+    const int64_t nl = c->n_local();
+    int64_t o = 0;
+    w.off_r = o; o = up(o + nl * 8);
+    w.off_z = o; o = up(o + nl * 8);
+    w.off_q = o; o = up(o + nl * 8);
+    w.off_p = o; o = up(o + world * w.n_pad * 8);
+    w.off_xg = o; o = up(o + (world > 1 ? world * w.n_pad * 8 : 0));
+    w.off_u = o; o = up(o + (k + 1) * 8);
+    w.off_mv = o; o = up(o + (matrix_free ? matvec_free_ws_bytes(c) : 0));
+    w.total = o + 256;
+    return w;
+}
+
+struct PcgOp {
+    mlffpc_ctx* ctx;
+    const double* K;
+    int64_t ld_k;
+    double lam;
+    void* mv_ws;
+    // q_local = A v,  A = -K + lam I;  v_full is the replicated n-vector
+    int apply(const double* v_full, double* q_local, cudaStream_t s) const {
+        if (K)
+            return launch_gemv_rows(K, ctx->n_local(), ctx->n, ld_k, v_full, q_local, -1.0, lam, ctx->row0(), s);
+        return matvec_free(ctx, v_full, q_local, -1.0, lam, mv_ws, s);
+    }
+};
+
+}  // namespace mlffpc
+
+using namespace mlffpc;
+
+extern "C" {
+
+int mlffpc_dot(mlffpc_ctx* ctx, const double* a, const double* b, int64_t n, double* out_host, void* stream) {
+    MLFFPC_REQUIRE(ctx && a && b && out_host && n >= 0, "dot: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned* counter = (unsigned*)(ctx->scal + S_COUNTER);
+    dot_kernel<<<vec_grid(n), VEC_THREADS, 0, s>>>(a, b, n, ctx->partials, counter, ctx->scal + S_TMP);
+    MLFFPC_LAUNCH_CHECK();
+    MLFFPC_TRY(comm_allreduce_sum(ctx->comm, ctx->scal + S_TMP, 1, s));
+    MLFFPC_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->scal + S_TMP, 8, cudaMemcpyDeviceToHost, s));
+    MLFFPC_CUDA(cudaStreamSynchronize(s));
+    *out_host = ctx->h_scal[0];
+    return MLFFPC_OK;
+}
+
+int mlffpc_pcg_workspace_bytes(mlffpc_ctx* ctx, int64_t k, int matrix_free, int64_t* bytes) {
+    MLFFPC_REQUIRE(ctx && bytes && k >= 0 && ctx->M > 0, "pcg_workspace_bytes: bad argument / geometry not set");
+    *bytes = pcg_layout(ctx, k, matrix_free != 0).total;
+    return MLFFPC_OK;
+}
+
+int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam, const double* T,
+               int64_t k, int64_t ld_t, double precon_sign, const double* b, double* x, double tol,
+               int64_t maxiter, double* out_host, double* resid_hist_host, void* workspace,
+               int64_t workspace_bytes, void* stream) {
+    MLFFPC_REQUIRE(ctx && ctx->M > 0, "pcg: geometry not set");
+    MLFFPC_REQUIRE(b && x && out_host && workspace, "pcg: NULL argument");
+    MLFFPC_REQUIRE(lam > 0.0 && tol > 0.0 && maxiter >= 0, "pcg: bad lam/tol/maxiter");
+    MLFFPC_REQUIRE(!K_local || ld_k >= ctx->n, "pcg: ld_k < n");
+    MLFFPC_REQUIRE(!T || (k > 0 && ld_t >= ctx->n_local()), "pcg: bad preconditioner dimensions");
+    const bool matrix_free = (K_local == nullptr);
+    const PcgWs w = pcg_layout(ctx, T ? k : 0, matrix_free);
+    MLFFPC_REQUIRE(workspace_bytes >= w.total, "pcg: workspace too small (%lld < %lld)",
+                   (long long)workspace_bytes, (long long)w.total);
+    const int world = ctx->comm.world;
+    const int64_t nl = ctx->n_local(), row0 = ctx->row0();
+    if (world > 1) {
+        const int64_t ppr = (ctx->M + world - 1) / world;
+        MLFFPC_REQUIRE(ctx->pt0 == ctx->comm.rank * ppr, "pcg: multi-GPU needs the ceil(M/world) point partition");
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    char* base = (char*)(((uintptr_t)workspace + 255) / 256 * 256);
+    double* r = (double*)(base + w.off_r);
+    double* z = (double*)(base + w.off_z);
+    double* q = (double*)(base + w.off_q);
+    double* p_full = (double*)(base + w.off_p);
+    double* p = p_full + row0;
+    double* xg = (world > 1) ? (double*)(base + w.off_xg) : nullptr;
+    double* u = (double*)(base + w.off_u);
+    PcgOp A{ctx, K_local, ld_k, lam, (void*)(base + w.off_mv)};
+    double* sc = ctx->scal;
+    unsigned* counter = (unsigned*)(sc + S_COUNTER);
+    const unsigned g = vec_grid(nl);
+
+    auto host_scalar = [&](int slot, double* out) -> int {
+        MLFFPC_CUDA(cudaMemcpyAsync(ctx->h_scal, sc + slot, 8, cudaMemcpyDeviceToHost, s));
+        MLFFPC_CUDA(cudaStreamSynchronize(s));
+        *out = ctx->h_scal[0];
+        return MLFFPC_OK;
+    };
+    // q = A x (x gathered when sharded), r = b - q, rr -> S_RR
+    auto true_residual = [&]() -> int {
+        const double* x_full = x;
+        if (world > 1) {
+            MLFFPC_CUDA(cudaMemsetAsync(xg + row0, 0, w.n_pad * 8, s));
+            MLFFPC_CUDA(cudaMemcpyAsync(xg + row0, x, nl * 8, cudaMemcpyDeviceToDevice, s));
+            MLFFPC_TRY(comm_allgather(ctx->comm, xg + row0, xg, w.n_pad * 8, s));
+            x_full = xg;
+        }
+        MLFFPC_TRY(A.apply(x_full, q, s));
+        residual_kernel<<<g, VEC_THREADS, 0, s>>>(b, q, r, nl, ctx->partials, counter, sc + S_RR);
+        MLFFPC_LAUNCH_CHECK();
+        return comm_allreduce_sum(ctx->comm, sc + S_RR, 1, s);
+    };
+
+    double bb = 0.0, rr = 0.0;
+    dot_kernel<<<g, VEC_THREADS, 0, s>>>(b, b, nl, ctx->partials, counter, sc + S_TMP);
+    MLFFPC_LAUNCH_CHECK();
+    MLFFPC_TRY(comm_allreduce_sum(ctx->comm, sc + S_TMP, 1, s));
+    MLFFPC_TRY(host_scalar(S_TMP, &bb));
+    const double bnrm2 = sqrt(bb);
+
+    MLFFPC_TRY(true_residual());
+    MLFFPC_TRY(host_scalar(S_RR, &rr));
+    double resid = sqrt(rr);
+    out_host[3] = bnrm2;
+    if (resid_hist_host) resid_hist_host[0] = resid;
+    if (resid <= tol) {  // legacy _get_atol probe
+        out_host[0] = 0; out_host[1] = resid; out_host[2] = 0;
+        return MLFFPC_OK;
+    }
+    const double atol = (bnrm2 == 0.0) ? tol : tol * bnrm2;
+    if (world > 1) MLFFPC_CUDA(cudaMemsetAsync(p_full, 0, (size_t)world * w.n_pad * 8, s));
+
+    int64_t it = 0;
+    int info = (int)(maxiter > 0x7fffffff ? 0x7fffffff : maxiter);
+    if (info == 0) info = 1;
+    while (it < maxiter) {
+        ++it;
+        double* rho = sc + (it & 1);
+        double* rho_prev = sc + ((it - 1) & 1);
+        // z = P r
+        if (T) {
+            MLFFPC_TRY(precon_apply(ctx, T, k, ld_t, lam, precon_sign, r, z, u, s));
+        } else {
+            MLFFPC_CUDA(cudaMemcpyAsync(z, r, nl * 8, cudaMemcpyDeviceToDevice, s));
+        }
+        dot_kernel<<<g, VEC_THREADS, 0, s>>>(r, z, nl, ctx->partials, counter, rho);
+        MLFFPC_LAUNCH_CHECK();
+        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, rho, 1, s));
+        update_p_kernel<<<g, VEC_THREADS, 0, s>>>(z, p, nl, rho, rho_prev, it == 1 ? 1 : 0);
+        MLFFPC_LAUNCH_CHECK();
+        if (world > 1) MLFFPC_TRY(comm_allgather(ctx->comm, p, p_full, w.n_pad * 8, s));
+        MLFFPC_TRY(A.apply(p_full, q, s));
+        dot_kernel<<<g, VEC_THREADS, 0, s>>>(p, q, nl, ctx->partials, counter, sc + S_PQ);
+        MLFFPC_LAUNCH_CHECK();
+        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, sc + S_PQ, 1, s));
+        update_xr_kernel<<<g, VEC_THREADS, 0, s>>>(x, r, p, q, nl, rho, sc + S_PQ, ctx->partials, counter, sc + S_RR);
+        MLFFPC_LAUNCH_CHECK();
+        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, sc + S_RR, 1, s));
+        MLFFPC_TRY(host_scalar(S_RR, &rr));
+        resid = sqrt(rr);
+        if (!(resid == resid)) {  // NaN: breakdown
+            set_error("pcg: residual became NaN at iteration %lld", (long long)it);
+            return MLFFPC_ERR_LINALG;
+        }
+        if (resid <= atol && it > 1) {
+            MLFFPC_TRY(true_residual());
+            MLFFPC_TRY(host_scalar(S_RR, &rr));
+            resid = sqrt(rr);
+        }
+        if (resid_hist_host) resid_hist_host[it] = resid;
+        if (resid <= atol) {
+            info = 0;
+            break;
+        }
+    }
+    out_host[0] = (double)it;
+    out_host[1] = resid;
+    out_host[2] = (double)info;
+    return MLFFPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+// Low-rank (Woodbury / Nystroem) preconditioner: factorisation and apply.
+//   factor (reference iterative_cholesky.py:141-143):  W = lam I + Lt Lt^T, L2 = chol(W), T = L2^{-1} Lt
+//   apply  (iterative_cholesky.py:145-148, iterative_solver.py:315-318):  z = sign (r - T^T (T r)) / lam
+// T is [k, n_local] row-major: "T r" streams k long rows, "T^T u" combines columns -- both coalesced,
+// 16 k n_local bytes of HBM traffic per apply.
+#include "common.cuh"
+
+namespace mlffpc {
+
+int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
+                 const double* r, double* z, double* u, cudaStream_t s) {
+    const int64_t nl = ctx->n_local();
+    // u = T r  (local part), summed over ranks
+    MLFFPC_TRY(launch_gemv_rows(T, k, nl, ld, r, u, 1.0, 0.0, 0, s));
+    MLFFPC_TRY(comm_allreduce_sum(ctx->comm, u, (size_t)k, s));
+    // z = sign (r - T^T u) / lam
+    MLFFPC_TRY(launch_tgemv_cols(T, k, nl, ld, u, z, 1, r, sign / lam, ctx->num_sms, s));
+    return MLFFPC_OK;
+}
+
+__global__ void scale_copy_kernel(const double* __restrict__ r, double* __restrict__ z, int64_t n, double a) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) z[t] = a * r[t];
+}
+
+}  // namespace mlffpc
+
+using namespace mlffpc;
+
+extern "C" {
+
+int mlffpc_woodbury_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, double lam, double* W,
+                           void* stream) {
+    MLFFPC_REQUIRE(ctx && ctx->M > 0, "woodbury_factor: geometry not set");
+    MLFFPC_REQUIRE(Lt && W && k > 0 && ld >= ctx->n_local(), "woodbury_factor: bad argument");
+    MLFFPC_TRY(mlffpc_syrk_rows(ctx, Lt, k, ctx->n_local(), ld, lam, W, k, stream));
+    int info = 0;
+    MLFFPC_TRY(mlffpc_potrf_lower(ctx, W, k, k, &info, stream));
+    if (info != 0) {
+        set_error("%d-th leading minor of the array is not positive definite", info);
+        return MLFFPC_ERR_LINALG;
+    }
+    return mlffpc_trsm_rows(ctx, W, k, k, Lt, ctx->n_local(), ld, stream);
+}
+
+int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
+                        const double* r, double* z, double* u, void* stream) {
+    MLFFPC_REQUIRE(ctx && ctx->M > 0, "precon_apply: geometry not set");
+    MLFFPC_REQUIRE(r && z && lam > 0.0, "precon_apply: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (k == 0 || T == nullptr) {
+        const int64_t nl = ctx->n_local();
+        scale_copy_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, s>>>(r, z, nl, sign / lam);
+        MLFFPC_LAUNCH_CHECK();
+        return MLFFPC_OK;
+    }
+    MLFFPC_REQUIRE(u && ld >= ctx->n_local(), "precon_apply: bad argument");
+    return precon_apply(ctx, T, k, ld, lam, sign, r, z, u, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,280 @@
+"""Device engine: one ``mlffpc_ctx`` + the torch CUDA tensors that back it.
+
+PyTorch is only the buffer/stream/process-group plumbing here; all arithmetic happens in
+libmlffpc.so (hand-written sm_100a CUDA) through the C ABI of include/mlffpc.h.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .desc import desc_perms_from_tril_perms_lin, n_atoms_from_dim_d
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def atom_perms_from_desc_perms(desc_perms, n_atoms):
+    """Recover the atom permutations P_p from descriptor permutations pi_p (the inverse of
+    ``Desc.perm``, utils/desc.py:360-389): the image of atom x is the atom common to the images of two
+    pairs that contain x.  For N = 2 the identity is returned (both choices give the same pi)."""
+    desc_perms = np.asarray(desc_perms)
+    S, D = desc_perms.shape
+    a, b = np.tril_indices(n_atoms, k=-1)
+    if n_atoms < 3:
+        return np.tile(np.arange(n_atoms, dtype=np.int32), (S, 1))
+    pair_of = {}
+    for d in range(D):
+        pair_of[(a[d], b[d])] = d
+        pair_of[(b[d], a[d])] = d
+    out = np.zeros((S, n_atoms), dtype=np.int32)
+    for p in range(S):
+        for x in range(n_atoms):
+            others = [y for y in range(n_atoms) if y != x][:2]
+            imgs = []
+            for y in others:
+                e = desc_perms[p, pair_of[(x, y)]]
+                imgs.append({int(a[e]), int(b[e])})
+            common = imgs[0] & imgs[1]
+            assert len(common) == 1, 'descriptor permutation is not induced by an atom permutation'
+            out[p, x] = common.pop()
+    return out
+
+
+def shard_points(M, rank, world):
+    """Row-block partition by training points: rank r owns [r*ceil(M/W), min((r+1)*ceil(M/W), M))."""
+    ppr = (M + world - 1) // world
+    pt0, pt1 = rank * ppr, min((rank + 1) * ppr, M)
+    if pt0 >= pt1:
+        raise ValueError('more ranks (%d) than training-point blocks (M = %d)' % (world, M))
+    return pt0, pt1
+
+
+class Engine(object):
+    """Geometry-bound solver context on one GPU (one rank of a row-block sharded job)."""
+
+    def __init__(self, R_desc, R_d_desc, tril_perms_lin, sig, perms=None, device=None, rank=0, world=1,
+                 init_comm=None):
+        if not torch.cuda.is_available():
+            raise _lib.MlffpcError('mlff_preconditioner_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        self.lib = _lib.load()
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        torch.cuda.set_device(self.device)
+        self.rank, self.world = rank, world
+        R_desc = np.ascontiguousarray(R_desc, dtype=np.float64)
+        R_d_desc = np.ascontiguousarray(R_d_desc, dtype=np.float64)
+        self.M, self.D = R_desc.shape
+        self.N = n_atoms_from_dim_d(self.D)
+        assert R_d_desc.shape == (self.M, self.D, 3)
+        self.dim_i = 3 * self.N
+        self.n = self.M * self.dim_i
+        self.sig = float(sig)
+        dperms = desc_perms_from_tril_perms_lin(tril_perms_lin, self.D)
+        self.S = dperms.shape[0]
+        if perms is None:
+            aperms = atom_perms_from_desc_perms(dperms, self.N)
+        else:
+            aperms = np.ascontiguousarray(perms, dtype=np.int32)
+            assert aperms.shape == (self.S, self.N)
+        self.pt0, self.pt1 = shard_points(self.M, rank, world)
+        self.n_local = (self.pt1 - self.pt0) * self.dim_i
+        self.row0 = self.pt0 * self.dim_i
+        self.h2d_bytes = R_desc.nbytes + R_d_desc.nbytes + dperms.nbytes + aperms.nbytes
+
+        self._R_desc = torch.from_numpy(R_desc).to(self.device)
+        self._R_d_desc = torch.from_numpy(R_d_desc).to(self.device)
+        self._dperms = torch.from_numpy(dperms).to(self.device)
+        self._aperms = torch.from_numpy(aperms).to(self.device)
+
+        ctx = ctypes.c_void_p()
+        _lib.check(self.lib.mlffpc_create(ctypes.byref(ctx), self.device.index))
+        self.ctx = ctx
+        if world > 1:
+            if init_comm is None:
+                raise ValueError('world > 1 needs init_comm (see dist.init_engine_comm)')
+            init_comm(self)
+        nbytes = ctypes.c_int64()
+        _lib.check(self.lib.mlffpc_geometry_workspace_bytes(self.M, self.N, self.S, ctypes.byref(nbytes)))
+        self._geo_ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.mlffpc_set_geometry(
+            self.ctx, self.M, self.N, self.S, _ptr(self._R_desc), _ptr(self._R_d_desc), _ptr(self._dperms),
+            _ptr(self._aperms), self.sig, self.pt0, self.pt1, _ptr(self._geo_ws), nbytes.value, self._stream()))
+        self._ws_cache = {}
+
+    # ---- plumbing -------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ws(self, key, nbytes):
+        t = self._ws_cache.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self._ws_cache[key] = t
+        return t
+
+    def empty(self, *shape):
+        return torch.empty(*shape, dtype=torch.float64, device=self.device)
+
+    def close(self):
+        if getattr(self, 'ctx', None) is not None and self.ctx:
+            self.lib.mlffpc_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- kernel entries -------------------------------------------------------------------
+    def kernel_diag(self):
+        """-diag(K) on the local rows (iterative_cholesky.py:241-373)."""
+        out = self.empty(self.n_local)
+        _lib.check(self.lib.mlffpc_kernel_diag(self.ctx, _ptr(out), self._stream()))
+        return out
+
+    def kernel_assemble(self, out=None):
+        """Explicit local rows K[row0:row0+n_local, :] (train.py:1121-1308)."""
+        if out is None:
+            out = self.empty(self.n_local, self.n)
+        assert out.shape == (self.n_local, self.n) and out.stride(1) == 1
+        _lib.check(self.lib.mlffpc_kernel_assemble(self.ctx, _ptr(out), out.stride(0), self._stream()))
+        return out
+
+    def kernel_columns(self, cols, scale=1.0, out=None):
+        """Transposed column panel out[c, r] = scale*K[row0 + r, cols[c]]; cols: int64 tensor/array."""
+        if not torch.is_tensor(cols):
+            cols = torch.as_tensor(np.asarray(cols, dtype=np.int64), device=self.device)
+        cols = cols.to(device=self.device, dtype=torch.int64).contiguous()
+        b = cols.numel()
+        if out is None:
+            out = self.empty(b, self.n_local)
+        assert out.shape[0] == b and out.shape[1] == self.n_local and out.stride(1) == 1
+        _lib.check(self.lib.mlffpc_kernel_columns(self.ctx, _ptr(cols), b, _ptr(out), out.stride(0), float(scale),
+                                                  ctypes.c_void_p(0), 0, self._stream()))
+        return out
+
+    # ---- operators ------------------------------------------------------------------------
+    def gemv(self, K, x, alpha=1.0, shift=0.0, x_off=0, out=None):
+        n_rows, n_cols = K.shape
+        assert K.stride(1) == 1 and x.is_contiguous() and x.numel() >= n_cols
+        if out is None:
+            out = self.empty(n_rows)
+        _lib.check(self.lib.mlffpc_gemv(self.ctx, _ptr(K), n_rows, n_cols, K.stride(0), _ptr(x), _ptr(out),
+                                        float(alpha), float(shift), int(x_off), self._stream()))
+        return out
+
+    def matvec_free(self, v, alpha=1.0, shift=0.0, out=None):
+        """alpha*(K v)_local + shift*v_local for the full n-vector v (predict.py:400-449,997-1052)."""
+        assert v.numel() >= self.n and v.is_contiguous()
+        if out is None:
+            out = self.empty(self.n_local)
+        nb = ctypes.c_int64()
+        _lib.check(self.lib.mlffpc_matvec_free_workspace_bytes(self.ctx, ctypes.byref(nb)))
+        ws = self._ws('mv', nb.value)
+        _lib.check(self.lib.mlffpc_matvec_free(self.ctx, _ptr(v), _ptr(out), float(alpha), float(shift), _ptr(ws),
+                                               nb.value, self._stream()))
+        return out
+
+    # ---- dense ----------------------------------------------------------------------------
+    def dgemm(self, A, B, trans_b=False, alpha=1.0, beta=0.0, out=None):
+        m, k = A.shape
+        n = B.shape[0] if trans_b else B.shape[1]
+        assert (B.shape[1] if trans_b else B.shape[0]) == k
+        assert A.stride(1) == 1 and B.stride(1) == 1
+        if out is None:
+            out = self.empty(m, n)
+        _lib.check(self.lib.mlffpc_dgemm(self.ctx, 1 if trans_b else 0, m, n, k, float(alpha), _ptr(A), A.stride(0),
+                                         _ptr(B), B.stride(0), float(beta), _ptr(out), out.stride(0), self._stream()))
+        return out
+
+    def syrk_rows(self, X, shift=0.0):
+        m, nc = X.shape
+        W = self.empty(m, m)
+        _lib.check(self.lib.mlffpc_syrk_rows(self.ctx, _ptr(X), m, nc, X.stride(0), float(shift), _ptr(W), m,
+                                             self._stream()))
+        return W
+
+    def potrf_lower(self, W, raise_on_fail=True):
+        """In-place lower Cholesky; returns LAPACK-style info (0 = ok)."""
+        m = W.shape[0]
+        info = ctypes.c_int()
+        _lib.check(self.lib.mlffpc_potrf_lower(self.ctx, _ptr(W), m, W.stride(0), ctypes.byref(info), self._stream()))
+        if info.value != 0 and raise_on_fail:
+            raise np.linalg.LinAlgError('%d-th leading minor of the array is not positive definite' % info.value)
+        return info.value
+
+    def trsm_rows(self, Lf, X):
+        m = Lf.shape[0]
+        assert X.shape[0] == m and X.stride(1) == 1
+        _lib.check(self.lib.mlffpc_trsm_rows(self.ctx, _ptr(Lf), m, Lf.stride(0), _ptr(X), X.shape[1], X.stride(0),
+                                             self._stream()))
+        return X
+
+    def allreduce_sum_(self, t):
+        _lib.check(self.lib.mlffpc_allreduce_sum(self.ctx, _ptr(t), t.numel(), self._stream()))
+        return t
+
+    # ---- pivoted partial Cholesky ---------------------------------------------------------
+    def pchol_build(self, k, diag=None, forced_pivots=None, want_times=True):
+        """(Lt[k, n_local], index_columns[n] int64, residual diag, step_seconds[k])."""
+        k = int(k)
+        if diag is None:
+            diag = self.kernel_diag()
+        else:
+            diag = diag.clone()
+        Lt = torch.zeros((k, self.n_local), dtype=torch.float64, device=self.device)
+        idx = torch.empty(self.n, dtype=torch.int64, device=self.device)
+        nb = ctypes.c_int64()
+        _lib.check(self.lib.mlffpc_pchol_workspace_bytes(self.ctx, k, ctypes.byref(nb)))
+        ws = self._ws('pchol', nb.value)
+        times = (ctypes.c_float * max(k, 1))() if want_times else None
+        fp = None
+        if forced_pivots is not None:
+            fp = torch.as_tensor(np.asarray(forced_pivots, dtype=np.int64), device=self.device)
+        _lib.check(self.lib.mlffpc_pchol_build(self.ctx, k, _ptr(Lt), max(self.n_local, 1), _ptr(diag), _ptr(idx),
+                                               _ptr(fp), times, _ptr(ws), nb.value, self._stream()))
+        step_s = np.frombuffer(times, dtype=np.float32)[:k].astype(np.float64) * 1e-3 if want_times else None
+        return Lt, idx, diag, step_s
+
+    # ---- preconditioner -------------------------------------------------------------------
+    def woodbury_factor_(self, Lt, lam):
+        """In place: Lt -> T = chol(lam I + Lt Lt^T)^{-1} Lt (iterative_cholesky.py:141-143)."""
+        k = Lt.shape[0]
+        W = self.empty(k, k)
+        _lib.check(self.lib.mlffpc_woodbury_factor(self.ctx, _ptr(Lt), k, Lt.stride(0), float(lam), _ptr(W),
+                                                   self._stream()))
+        return Lt
+
+    def precon_apply(self, T, lam, sign, r, out=None):
+        if out is None:
+            out = self.empty(self.n_local)
+        k = 0 if T is None else T.shape[0]
+        u = self.empty(max(k, 1))
+        _lib.check(self.lib.mlffpc_precon_apply(self.ctx, _ptr(T), k, 0 if T is None else T.stride(0), float(lam),
+                                                float(sign), _ptr(r), _ptr(out), _ptr(u), self._stream()))
+        return out
+
+    # ---- PCG ------------------------------------------------------------------------------
+    def pcg(self, b, lam, tol, maxiter, K_local=None, T=None, precon_sign=1.0, x0=None, want_hist=False):
+        """Returns (x_local, iters, resid, info, bnrm2[, hist])."""
+        k = 0 if T is None else T.shape[0]
+        x = torch.zeros(self.n_local, dtype=torch.float64, device=self.device) if x0 is None else x0.clone()
+        nb = ctypes.c_int64()
+        _lib.check(self.lib.mlffpc_pcg_workspace_bytes(self.ctx, k, 1 if K_local is None else 0, ctypes.byref(nb)))
+        ws = self._ws('pcg', nb.value)
+        out = (ctypes.c_double * 4)()
+        hist = None
+        if want_hist:
+            hist = np.full(int(maxiter) + 1, np.nan)
+        _lib.check(self.lib.mlffpc_pcg(
+            self.ctx, _ptr(K_local), 0 if K_local is None else K_local.stride(0), float(lam), _ptr(T), k,
+            0 if T is None else T.stride(0), float(precon_sign), _ptr(b), _ptr(x), float(tol), int(maxiter), out,
+            hist.ctypes.data_as(ctypes.c_void_p) if hist is not None else ctypes.c_void_p(0), _ptr(ws), nb.value,
+            self._stream()))
+        res = (x, int(out[0]), float(out[1]), int(out[2]), float(out[3]))
+        if want_hist:
+            return res + (hist[:int(out[0]) + 1],)
+        return res
