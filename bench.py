@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: fp64 PCG time-to-solution on the assembled sGDML kernel.
+
+One "step" = one full solve of the named workload: pivoted-Cholesky preconditioner build (on-the-fly
+columns) + Woodbury factorisation + explicit kernel assembly + PCG to the relative residual `tol`.
+Default workload (BASELINE.json configs[1]): synthetic ethanol-size geometries, N = 9 atoms, M = 4000
+training points -> n = 108 000 (K = 93.3 GB fp64, assembled in HBM), k = rule-of-thumb rank, tol 1e-6.
+
+  value : seconds per solve with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same through the reference-facing call Iterative.solve(task, R_desc, R_d_desc, ...) with HOST
+          numpy buffers -- H2D of descriptors / labels and D2H of the coefficients inside the timed region
+  roofline : the assembled GEMV (dominant kernel), algorithmic bytes 8*n_local*n + 8*n + 8*n_local per launch
+             over its mean CUDA-event duration inside the timed solves
+  cpu_baseline : the reference's CPU algorithm (oracle port, torch-CPU matvec = the reference's fastest CPU
+             route) timed on this box's host cores on a bounded sample and extrapolated to the full solve
+
+`--impl reference` prints the CPU arm alone (rank 0 only under torchrun).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (structure, M, tol)
+    'cfg2': ('ethanol', 4000, 1e-6),
+    'cfg2_mid': ('ethanol', 1500, 1e-6),
+    'small': ('ethanol', 300, 1e-6),
+}
+CONSTANTS_FILE = os.path.join(ROOT, 'bench_constants.json')
+
+
+def rule_of_thumb(n, k_min, m):
+    """k = (k_min^m * m * n^2 / 2)^(1/(2+m))  (reference src/tools/plot_data.py:1254-1258)."""
+    return int((k_min ** m * m * n ** 2 / 2) ** (1.0 / (2 + m)))
+
+
+def make_inputs(workload, M_override=None):
+    from mlff_preconditioner_b200 import synthetic
+    from mlff_preconditioner_b200.desc import Desc, tril_perms_lin_from_perms
+
+    kind, M, tol = WORKLOADS[workload]
+    if M_override:
+        M = M_override
+    ds = synthetic.make_dataset(kind, M, seed=0)
+    N = ds['R'].shape[1]
+    perms = np.arange(N)[None]
+    desc = Desc(N)
+    tpl = tril_perms_lin_from_perms(perms, desc)
+    R_desc, R_d_desc = desc.from_R(ds['R'].reshape(M, -1))
+    y = ds['F'].ravel().copy()
+    y_std = np.std(y)
+    y /= y_std
+    n = 3 * N * M
+    k = min(rule_of_thumb(n, 10, 0.87), n // 4)  # ethanol parameters (plot_data.py:677-706)
+    task = {'R_train': ds['R'], 'F_train': ds['F'], 'sig': 10, 'lam': 1e-10, 'perms': perms, 'use_E_cstr': False,
+            'solver_tol': tol, 'n_inducing_pts_init': 25, 'truncated_cholesky': 1500}
+    return dict(kind=kind, M=M, N=N, n=n, k=k, tol=tol, task=task, R_desc=R_desc, R_d_desc=R_d_desc, tpl=tpl,
+                y=y, y_std=y_std, perms=perms)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
+            'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            f = [x.strip() for x in s.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(nm)
+        busy = [c for c in sm if c > 0]
+        return {'sm_mhz': float(np.median(busy)) if busy else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_reference_sample(inp, cg_iters, light=False):
+    """Bounded sample of the reference's CPU algorithm on this box, extrapolated to one full solve.
+
+    Per-operation costs are measured with the oracle port of the reference (oracle/sgdml_oracle.py; the
+    kernel matvec through torch-CPU ops exactly like the reference's use_torch=True path without a GPU):
+      t_mv   one K_op.matvec at full n                       (also the cost of one pivot column: get_col = K_op e_i)
+      t_sch  one pivot step's Schur update at m = k/2         (incomplete_cholesky.py:66-78)
+      t_fac  Woodbury factorisation at rank k' << k, scaled by (k/k')^2   (iterative_cholesky.py:141-143)
+      t_app  one preconditioner apply at rank k', scaled by k/k'            (iterative_cholesky.py:145-148)
+    solve = k (t_mv + t_sch) + t_fac + cg_iters (t_mv + t_app)
+    """
+    import torch
+    from oracle import sgdml_oracle as orc
+
+    torch.set_num_threads(os.cpu_count())
+    n, k, M = inp['n'], inp['k'], inp['M']
+    rng = np.random.default_rng(0)
+    R_desc_t = torch.from_numpy(inp['R_desc'])
+    Xp_t = torch.from_numpy(orc.permuted_rows(inp['R_desc'], inp['tpl']).reshape(-1, inp['R_desc'].shape[1]))
+    v = rng.standard_normal(n)
+    reps_mv = 1 if light else 2
+    orc.kernel_matvec_torch_cpu(R_desc_t, Xp_t, inp['R_d_desc'], inp['tpl'], 10, v[:n])  # warm
+    t0 = time.perf_counter()
+    for _ in range(reps_mv):
+        orc.kernel_matvec_torch_cpu(R_desc_t, Xp_t, inp['R_d_desc'], inp['tpl'], 10, v)
+    t_mv = (time.perf_counter() - t0) / reps_mv
+
+    m_half = max(1, k // 2 if not light else k // 8)
+    L = np.ones((n, m_half))
+    idx = np.arange(n)
+    diag = np.ones(n)
+    col = np.ones(n)
+    t0 = time.perf_counter()
+    for _ in range(1 if light else 2):
+        i_pi = idx[1:]
+        schur = np.einsum('c,rc->r', L[0, :m_half], L[i_pi, :m_half])
+        newcol = (col[i_pi] - schur) / 2.0
+        diag[i_pi] -= newcol ** 2
+    t_sch = (time.perf_counter() - t0) / (1 if light else 2) * (k / 2.0) / m_half
+    del L
+
+    k_s = min(k, 256 if light else 512)
+    Ls = rng.standard_normal((n, k_s))
+    t0 = time.perf_counter()
+    T = orc.woodbury_factor(Ls, 1e-10)
+    t_fac = (time.perf_counter() - t0) * (k / k_s) ** 2
+    a = rng.standard_normal(n)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        orc.woodbury_apply(T, 1e-10, a)
+    t_app = (time.perf_counter() - t0) / 3 * (k / k_s)
+    total = k * (t_mv + t_sch) + t_fac + cg_iters * (t_mv + t_app)
+    detail = {'t_matvec_s': t_mv, 't_schur_step_s': t_sch, 't_factor_s': t_fac, 't_apply_s': t_app,
+              'k': k, 'cg_iters': cg_iters}
+    return total, detail
+
+
+def load_constants():
+    try:
+        return json.load(open(CONSTANTS_FILE))
+    except Exception:
+        return {}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    inp = make_inputs(args.workload, args.M)
+    consts = load_constants().get(args.workload, {})
+    cg_iters = int(consts.get('cg_iters', 1000))
+    src = 'bench_constants.json' if 'cg_iters' in consts else 'assumed (no GPU run recorded yet)'
+    for _ in range(args.warmup):
+        cpu_reference_sample(inp, cg_iters, light=True)
+    vals, detail = [], None
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        v, detail = cpu_reference_sample(inp, cg_iters)
+        vals.append(v)
+    wall = time.perf_counter() - t_wall
+    value = float(np.mean(vals))
+    sample = ('per step: 2 full-n torch-CPU kernel matvecs, 2 Schur-update steps at m=k/2, Woodbury factor at k\'=512 '
+              '(scaled (k/k\')^2), 3 applies at k\' (scaled k/k\'); extrapolated solve = k(t_mv+t_sch)+t_fac+iters(t_mv+t_app); '
+              'cg_iters=%d from %s' % (cg_iters, src))
+    line = {
+        'impl': 'reference', 'metric': 'pcg_time_to_solution', 'value': value, 'unit': 's', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / max(args.steps, 1),
+        'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(inp, args, 1),
+        'cpu_baseline': {'value': value, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample,
+                         'extrapolated': True, 'detail': detail},
+        'e2e': {'value': value, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(inp, args, world):
+    return {'workload': '%s: synthetic %s-size N=%d M=%d n=%d, assembled fp64 kernel (%.1f GB) row-block sharded over %d GPU(s), '
+                        "'cholesky' preconditioner k=%d, tol=%g, sig=10, lam=1e-10"
+                        % (args.workload, inp['kind'], inp['N'], inp['M'], inp['n'], 8.0 * inp['n'] ** 2 / 1e9, world,
+                           inp['k'], inp['tol']),
+            'kernel_mode': args.mode, 'n': inp['n'], 'k': inp['k'], 'tol': inp['tol'],
+            'l2_policy': 'inputs larger than L2: K (>= 11.7 GB per GPU) is re-assembled and streamed every step'}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    import __graft_entry__ as g
+
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    from mlff_preconditioner_b200 import _lib
+    from mlff_preconditioner_b200.dist import allgather_rows, init_engine_comm
+    from mlff_preconditioner_b200.engine import Engine
+    from mlff_preconditioner_b200.solvers.iterative_solver import Iterative
+
+    lib = _lib.load()
+    inp = make_inputs(args.workload, args.M)
+    n, k = inp['n'], inp['k']
+    frac = (k + 0.5) / n  # int(frac * n) == k
+    task = dict(inp['task'])
+    task['kernel_mode'] = args.mode
+    dev = torch.device('cuda', local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm: inputs in HBM before the timed region --------------------------------
+    eng = Engine(inp['R_desc'], inp['R_d_desc'], inp['tpl'], 10, perms=inp['perms'], rank=rank, world=world,
+                 init_comm=init_engine_comm if world > 1 else None)
+    y_t = torch.as_tensor(inp['y'], device=dev)
+    if args.mode == 'assembled':
+        task['_K_buffer'] = eng.empty(eng.n_local, eng.n)
+    n_ind = min(inp['M'], int(max(np.ceil(frac * inp['M']), 1)))
+    stats = []
+
+    def one_step():
+        it = Iterative(None, None)
+        out = it.solve_device(task, eng, y_t, frac, 'cholesky', n_ind)
+        return it, out
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = lib.mlffpc_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        it, out = one_step()
+        stats.append((it.timings, out[1], out[2], out[3]))
+    ev1.record()
+    barrier()
+    launches = lib.mlffpc_launch_count() - launches0
+    clocks = sampler.stop()
+    dev_s = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    value = dev_s / args.steps
+    tm, iters, resid, info = stats[-1]
+    x_last = out[0]
+    alphas_dev = (-allgather_rows(eng, x_last)).cpu().numpy()
+
+    # roofline of the dominant kernel: the operator inside the timed PCG loops
+    op_ms = sum(s[0]['pcg_stats']['op_ms'] for s in stats)
+    op_calls = sum(s[0]['pcg_stats']['op_calls'] for s in stats)
+    pre_ms = sum(s[0]['pcg_stats']['precon_ms'] for s in stats)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+    avg_op_s = op_ms * 1e-3 / max(op_calls, 1)
+    if args.mode == 'assembled':
+        alg_bytes = 8.0 * eng.n_local * eng.n + 8.0 * eng.n + 8.0 * eng.n_local
+        achieved = alg_bytes / avg_op_s / 1e9
+        roofline = {'bound': 'hbm', 'kernel': 'gemv_rows_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                    'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                    'bytes_per_launch': alg_bytes, 'avg_launch_ms': avg_op_s * 1e3, 'launches_timed': op_calls}
+    else:
+        flops = 8.0 * (eng.pt1 - eng.pt0) * eng.M * eng.S * eng.D
+        roofline = {'bound': 'fp64', 'kernel': 'matvec_free (pairs + DMMA GEMM)', 'achieved': flops / avg_op_s / 1e12,
+                    'peak': 40.0, 'unit': 'TFLOP/s', 'frac': flops / avg_op_s / 1e12 / 40.0, 'traffic': None,
+                    'peak_source': 'nominal B200 fp64 (no measured fp64 peak in MEASURED_PEAKS.json)',
+                    'avg_launch_ms': avg_op_s * 1e3, 'launches_timed': op_calls}
+    phases = {'preconditioner_s': tm['preconditioner'], 'pchol_build_s': tm.get('pchol_build'),
+              'assemble_s': tm['assemble'], 'cg_s': tm['cg'], 'cg_iters': iters, 'resid': resid,
+              'rel_resid': resid / np.linalg.norm(inp['y']), 'converged': info == 0,
+              'precon_apply_avg_ms': pre_ms / max(op_calls, 1)}
+
+    # ---- end-to-end arm: host numpy in, host numpy out, through Iterative.solve -----------------------
+    del it, out
+    task.pop('_K_buffer', None)
+    torch.cuda.empty_cache()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h2d = d2h = 0
+    for rep in range(1 + e2e_steps):  # one warm-up
+        if rep == 1:
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        its = Iterative(None, None)
+        res = its.solve(task, inp['R_desc'], inp['R_d_desc'], inp['tpl'], inp['y'], inp['y_std'],
+                        break_percentage=frac, str_preconditioner='cholesky')
+        h2d, d2h = its.timings['h2d_bytes'], its.timings['d2h_bytes']
+        its.engine.close()
+        del its
+    e1.record()
+    barrier()
+    e2e_s = max_over_ranks(e0.elapsed_time(e1) * 1e-3) / e2e_steps
+    agree = float(np.linalg.norm(res[0] - alphas_dev) / np.linalg.norm(alphas_dev))
+
+    line = {
+        'metric': 'pcg_time_to_solution', 'value': value, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': value * 1e3, 'higher_is_better': False, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(inp, args, world),
+        'clocks': clocks,
+        'e2e': {'value': e2e_s, 'unit': 's', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'steps': e2e_steps, 'api': 'Iterative.solve(task, R_desc, R_d_desc, tril_perms_lin, y, y_std, ...)',
+                'alphas_rel_diff_vs_device_arm': agree},
+        'gpu_launches': int(launches),
+        'roofline': roofline,
+        'phases': phases,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        total, detail = cpu_reference_sample(inp, iters)
+        line['cpu_baseline'] = {
+            'value': total, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'port', 'extrapolated': True,
+            'sample': '2 full-n torch-CPU kernel matvecs, 2 Schur-update steps at m=k/2, Woodbury factor at k\'=512 '
+                      '(scaled (k/k\')^2), 3 applies at k\' (scaled k/k\'); solve = k(t_mv+t_sch)+t_fac+iters(t_mv+t_app) '
+                      'with the GPU run\'s k and iteration count',
+            'detail': detail}
+        consts = load_constants()
+        consts.setdefault(args.workload, {})['cg_iters'] = int(iters)
+        try:
+            json.dump(consts, open(CONSTANTS_FILE, 'w'), indent=1)
+        except OSError:
+            pass
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--M', type=int, default=None, help='override the number of training points')
+    ap.add_argument('--mode', default='assembled', choices=['assembled', 'matrix_free'])
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

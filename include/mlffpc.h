@@ -35,6 +35,7 @@ typedef struct mlffpc_ctx mlffpc_ctx;
 
 /* ---------------------------------------------------------------- lifecycle ---- */
 int mlffpc_version(void);
+int64_t mlffpc_launch_count(void); /* kernels launched by this library so far (process-wide) */
 const char* mlffpc_last_error(void);
 int mlffpc_create(mlffpc_ctx** out, int device);
 int mlffpc_destroy(mlffpc_ctx* ctx);
@@ -145,7 +146,8 @@ int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld,
  *   K_local: explicit local rows [n_local, n] (ld_k) or NULL for the matrix-free operator
  *   T: preconditioner factor [k, n_local] or NULL (identity); precon_sign as in mlffpc_precon_apply
  *   b, x: local rows (x in: initial guess, out: solution)
- *   out_host[4] (host doubles): iterations, final ||r||, info (0 converged), ||b||
+ *   out_host[8] (host doubles): iterations, final ||r||, info (0 converged), ||b||,
+ *       summed operator ms, operator calls, summed preconditioner ms (CUDA events), reserved
  *   resid_hist_host: NULL or host double[maxiter+1] receiving ||r|| per iteration
  * Workspace: mlffpc_pcg_workspace_bytes. */
 int mlffpc_pcg_workspace_bytes(mlffpc_ctx* ctx, int64_t k, int matrix_free, int64_t* bytes);

@@ -53,7 +53,8 @@ SIGNATURES = {
                    c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     'mlffpc_dot': [c_ptr, c_ptr, c_ptr, c_i64, ctypes.POINTER(c_dbl), c_ptr],
 }
-NON_INT_RETURNS = {'mlffpc_version': (c_int, []), 'mlffpc_last_error': (c_str, [])}
+NON_INT_RETURNS = {'mlffpc_version': (c_int, []), 'mlffpc_last_error': (c_str, []),
+                   'mlffpc_launch_count': (c_i64, [])}
 
 _lib = None
 

@@ -11,6 +11,7 @@ namespace mlffpc {
 
 // ---- error plumbing: every extern "C" entry returns a status, message via mlffpc_last_error() ----
 void set_error(const char* fmt, ...);
+extern long long g_launches;  // kernels launched by this library (bench.py's gpu_launches)
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define MLFFPC_CUDA(call)                                                          \
@@ -21,6 +22,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define MLFFPC_LAUNCH_CHECK()                                                      \
     do {                                                                           \
+        ++mlffpc::g_launches;                                                      \
         cudaError_t _e = cudaGetLastError();                                       \
         if (_e != cudaSuccess) return mlffpc::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
     } while (0)

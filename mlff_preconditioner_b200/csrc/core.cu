@@ -8,6 +8,7 @@
 namespace mlffpc {
 
 static thread_local char g_err[1024] = "";
+long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -101,6 +102,8 @@ using namespace mlffpc;
 extern "C" {
 
 int mlffpc_version(void) { return 100; }
+
+int64_t mlffpc_launch_count(void) { return (int64_t)g_launches; }
 
 const char* mlffpc_last_error(void) { return g_err; }
 

@@ -217,10 +217,18 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     if (resid_hist_host) resid_hist_host[0] = resid;
     if (resid <= tol) {  // legacy _get_atol probe
         out_host[0] = 0; out_host[1] = resid; out_host[2] = 0;
+        out_host[4] = out_host[5] = out_host[6] = 0;
         return MLFFPC_OK;
     }
     const double atol = (bnrm2 == 0.0) ? tol : tol * bnrm2;
     if (world > 1) MLFFPC_CUDA(cudaMemsetAsync(p_full, 0, (size_t)world * w.n_pad * 8, s));
+
+    // per-iteration CUDA-event timing of the operator and the preconditioner (the host syncs once per
+    // iteration anyway, so reading the events costs nothing extra)
+    cudaEvent_t ev[4];
+    for (auto& e : ev) MLFFPC_CUDA(cudaEventCreate(&e));
+    double op_ms = 0.0, pre_ms = 0.0;
+    int64_t op_calls = 0;
 
     int64_t it = 0;
     int info = (int)(maxiter > 0x7fffffff ? 0x7fffffff : maxiter);
@@ -230,18 +238,22 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
         double* rho = sc + (it & 1);
         double* rho_prev = sc + ((it - 1) & 1);
         // z = P r
+        cudaEventRecord(ev[0], s);
         if (T) {
             MLFFPC_TRY(precon_apply(ctx, T, k, ld_t, lam, precon_sign, r, z, u, s));
         } else {
             MLFFPC_CUDA(cudaMemcpyAsync(z, r, nl * 8, cudaMemcpyDeviceToDevice, s));
         }
+        cudaEventRecord(ev[1], s);
         dot_kernel<<<g, VEC_THREADS, 0, s>>>(r, z, nl, ctx->partials, counter, rho);
         MLFFPC_LAUNCH_CHECK();
         MLFFPC_TRY(comm_allreduce_sum(ctx->comm, rho, 1, s));
         update_p_kernel<<<g, VEC_THREADS, 0, s>>>(z, p, nl, rho, rho_prev, it == 1 ? 1 : 0);
         MLFFPC_LAUNCH_CHECK();
         if (world > 1) MLFFPC_TRY(comm_allgather(ctx->comm, p, p_full, w.n_pad * 8, s));
+        cudaEventRecord(ev[2], s);
         MLFFPC_TRY(A.apply(p_full, q, s));
+        cudaEventRecord(ev[3], s);
         dot_kernel<<<g, VEC_THREADS, 0, s>>>(p, q, nl, ctx->partials, counter, sc + S_PQ);
         MLFFPC_LAUNCH_CHECK();
         MLFFPC_TRY(comm_allreduce_sum(ctx->comm, sc + S_PQ, 1, s));
@@ -249,6 +261,11 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
         MLFFPC_LAUNCH_CHECK();
         MLFFPC_TRY(comm_allreduce_sum(ctx->comm, sc + S_RR, 1, s));
         MLFFPC_TRY(host_scalar(S_RR, &rr));
+        {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) pre_ms += ms;
+            if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) { op_ms += ms; ++op_calls; }
+        }
         resid = sqrt(rr);
         if (!(resid == resid)) {  // NaN: breakdown
             set_error("pcg: residual became NaN at iteration %lld", (long long)it);
@@ -265,9 +282,13 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
             break;
         }
     }
+    for (auto& e : ev) cudaEventDestroy(e);
     out_host[0] = (double)it;
     out_host[1] = resid;
     out_host[2] = (double)info;
+    out_host[4] = op_ms;
+    out_host[5] = (double)op_calls;
+    out_host[6] = pre_ms;
     return MLFFPC_OK;
 }
 

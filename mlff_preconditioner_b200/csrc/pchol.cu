@@ -301,6 +301,7 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
             prev_parts = (int)((nl + 31) / 32);
             pchol_update_kernel<8><<<prev_parts, PCHOL_THREADS, 0, s>>>(Lt, ld, m, nl, row0, col, lrow, piv_idx, piv_val, diag, pos, partials);
         }
+        g_launches += (m > 0) ? 4 : 4;  // scan|gather + reduce + select + update (the column kernel counts itself)
         {
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) { status = cuda_fail(e, "pchol step", __FILE__, __LINE__); break; }

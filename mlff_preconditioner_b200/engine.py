@@ -265,7 +265,7 @@ class Engine(object):
         nb = ctypes.c_int64()
         _lib.check(self.lib.mlffpc_pcg_workspace_bytes(self.ctx, k, 1 if K_local is None else 0, ctypes.byref(nb)))
         ws = self._ws('pcg', nb.value)
-        out = (ctypes.c_double * 4)()
+        out = (ctypes.c_double * 8)()
         hist = None
         if want_hist:
             hist = np.full(int(maxiter) + 1, np.nan)
@@ -274,6 +274,7 @@ class Engine(object):
             0 if T is None else T.stride(0), float(precon_sign), _ptr(b), _ptr(x), float(tol), int(maxiter), out,
             hist.ctypes.data_as(ctypes.c_void_p) if hist is not None else ctypes.c_void_p(0), _ptr(ws), nb.value,
             self._stream()))
+        self.last_pcg_stats = {'op_ms': float(out[4]), 'op_calls': int(out[5]), 'precon_ms': float(out[6])}
         res = (x, int(out[0]), float(out[1]), int(out[2]), float(out[3]))
         if want_hist:
             return res + (hist[:int(out[0]) + 1],)

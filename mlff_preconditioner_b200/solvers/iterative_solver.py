@@ -139,39 +139,18 @@ class Iterative(object):
         need = eng.n_local * eng.n * 8 + 2 * max(k, 1) * eng.n_local * 8 + (2 << 30)
         return 'assembled' if need < free else 'matrix_free'
 
-    # ------------------------------------------------------------------ the solve step
-    def solve(self, task, R_desc, R_d_desc, tril_perms_lin, y, y_std, save_progr_callback=None,
-              break_percentage=None, str_preconditioner='', flag_eigvals=False):
-        start_solve_routine = timeit.default_timer()
-        n_train, n_atoms = task['R_train'].shape[:2]
-        n = 3 * n_train * n_atoms
+    # ------------------------------------------------------------------ device-resident solve
+    def solve_device(self, task, eng, y_t, break_percentage, str_preconditioner, n_inducing_pts, x0=None):
+        """Everything between the H2D of the inputs and the D2H of the solution: preconditioner build,
+        kernel operator, PCG.  ``y_t`` is the full right-hand side on the device.  Returns
+        ``(x_local, iters, resid, info, inducing_pts_idxs, info_cholesky, t_precon, t_cg)``."""
+        self.engine = eng
+        n, n_train, n_atoms = eng.n, eng.M, eng.N
         sig, lam = task['sig'], task['lam']
-
-        if task.get('use_E_cstr', False):
-            raise NotImplementedError('use_E_cstr=True is outside the hot-path contract (the reference GPU path '
-                                      'aborts as well, iterative_solver.py:834-836)')
-        if flag_eigvals:
-            raise NotImplementedError('flag_eigvals diagnostics (dev_utils.get_eigvals, O(n^3)) are out of scope')
-        if str_preconditioner in OUT_OF_CONTRACT:
-            raise NotImplementedError(f'str_preconditioner = {str_preconditioner} (full SVD, O(n^3)) is out of scope')
-        if 'inducing_pts_idxs' in task:
-            assert False, 'Nor applicable in this setting'  # iterative_solver.py:680
-        alphas0_F = task['alphas0_F'] if 'alphas0_F' in task else None
-        num_iters0 = task['solver_iters'] if 'solver_iters' in task else 0
-        if break_percentage is None:
-            n_inducing_pts_init = int(task['n_inducing_pts_init'])
-        else:
-            n_inducing_pts_init = int(max(np.ceil(break_percentage * n_train), 1))
-        n_inducing_pts = min(n_train, n_inducing_pts_init)
+        R_desc = R_d_desc = tril_perms_lin = None  # geometry lives in the engine
 
         def sync():
             torch.cuda.synchronize()
-
-        eng = self._make_engine(task, R_desc, R_d_desc, tril_perms_lin)
-        assert eng.n == n
-        y_t = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float64), device=eng.device)
-        h2d_bytes = eng.h2d_bytes + y_t.numel() * 8
-        sync()
 
         start_preconditioner = timeit.default_timer()
         info_cholesky = None
@@ -216,24 +195,20 @@ class Iterative(object):
         else:
             raise NotImplementedError(f'str_preconditioner = {str_preconditioner}')
         sync()
-        stop_preconditioner = timeit.default_timer()
-        total_time_preconditioner = stop_preconditioner - start_preconditioner
-        total_time_cholesky = total_time_preconditioner
+        total_time_preconditioner = timeit.default_timer() - start_preconditioner
         self.last_P_op = P_op
 
         # kernel operator: assembled row block or matrix-free
         k_rank = 0 if P_op.T is None else P_op.T.shape[0]
         mode = self._choose_kernel_mode(task, k_rank)
         t0 = timeit.default_timer()
-        self.K_local = eng.kernel_assemble() if mode == 'assembled' else None
+        self.K_local = None
+        if mode == 'assembled':
+            self.K_local = eng.kernel_assemble(out=task.get('_K_buffer'))
         sync()
         self.timings['assemble'] = timeit.default_timer() - t0
         self.timings['kernel_mode'] = mode
 
-        x0 = None
-        if alphas0_F is not None:
-            x0_full = torch.as_tensor(-np.asarray(alphas0_F, dtype=np.float64).ravel(), device=eng.device)
-            x0 = x0_full[eng.row0:eng.row0 + eng.n_local].contiguous()
         maxiter = 3 * n_atoms * n_train * 5  # :1002
         tic_start = timeit.default_timer()
         x, iters, resid, info, bnrm2 = eng.pcg(
@@ -241,6 +216,51 @@ class Iterative(object):
             K_local=self.K_local, T=P_op.T, precon_sign=P_op.sign, x0=x0)
         sync()
         total_time_cg = timeit.default_timer() - tic_start
+        self.timings.update(cg=total_time_cg, preconditioner=total_time_preconditioner, cg_iters=iters, k=k_rank,
+                            pcg_stats=dict(eng.last_pcg_stats))
+        return x, iters, resid, info, inducing_pts_idxs, info_cholesky, total_time_preconditioner, total_time_cg
+
+    # ------------------------------------------------------------------ the solve step
+    def solve(self, task, R_desc, R_d_desc, tril_perms_lin, y, y_std, save_progr_callback=None,
+              break_percentage=None, str_preconditioner='', flag_eigvals=False):
+        start_solve_routine = timeit.default_timer()
+        n_train, n_atoms = task['R_train'].shape[:2]
+        n = 3 * n_train * n_atoms
+        sig, lam = task['sig'], task['lam']
+
+        if task.get('use_E_cstr', False):
+            raise NotImplementedError('use_E_cstr=True is outside the hot-path contract (the reference GPU path '
+                                      'aborts as well, iterative_solver.py:834-836)')
+        if flag_eigvals:
+            raise NotImplementedError('flag_eigvals diagnostics (dev_utils.get_eigvals, O(n^3)) are out of scope')
+        if str_preconditioner in OUT_OF_CONTRACT:
+            raise NotImplementedError(f'str_preconditioner = {str_preconditioner} (full SVD, O(n^3)) is out of scope')
+        if 'inducing_pts_idxs' in task:
+            assert False, 'Nor applicable in this setting'  # iterative_solver.py:680
+        alphas0_F = task['alphas0_F'] if 'alphas0_F' in task else None
+        num_iters0 = task['solver_iters'] if 'solver_iters' in task else 0
+        if break_percentage is None:
+            n_inducing_pts_init = int(task['n_inducing_pts_init'])
+        else:
+            n_inducing_pts_init = int(max(np.ceil(break_percentage * n_train), 1))
+        n_inducing_pts = min(n_train, n_inducing_pts_init)
+
+        def sync():
+            torch.cuda.synchronize()
+
+        eng = self._make_engine(task, R_desc, R_d_desc, tril_perms_lin)
+        assert eng.n == n
+        y_t = torch.as_tensor(np.ascontiguousarray(y, dtype=np.float64), device=eng.device)
+        h2d_bytes = eng.h2d_bytes + y_t.numel() * 8
+        x0 = None
+        if alphas0_F is not None:
+            x0_full = torch.as_tensor(-np.asarray(alphas0_F, dtype=np.float64).ravel(), device=eng.device)
+            x0 = x0_full[eng.row0:eng.row0 + eng.n_local].contiguous()
+        sync()
+        (x, iters, resid, info, inducing_pts_idxs, info_cholesky, total_time_preconditioner,
+         total_time_cg) = self.solve_device(task, eng, y_t, break_percentage, str_preconditioner, n_inducing_pts, x0)
+        total_time_cholesky = total_time_preconditioner
+        k_rank = self.timings['k']
 
         alphas = (-allgather_rows(eng, x)).cpu().numpy()  # :1009
         d2h_bytes = alphas.nbytes
@@ -255,7 +275,6 @@ class Iterative(object):
                                  'total_time_preconditioner': total_time_preconditioner}
         if str_preconditioner == 'cholesky':
             info_iterative_solver.update(info_cholesky)
-        self.timings.update(cg=total_time_cg, preconditioner=total_time_preconditioner, solve=total_time_solve,
-                            cg_iters=iters, h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes, k=k_rank)
+        self.timings.update(solve=total_time_solve, h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes)
         train_rmse = resid / np.sqrt(len(y))
         return alphas, num_iters, resid, train_rmse, inducing_pts_idxs, is_conv, info_iterative_solver
