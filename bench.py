@@ -43,7 +43,7 @@ def rule_of_thumb(n, k_min, m):
     return int((k_min ** m * m * n ** 2 / 2) ** (1.0 / (2 + m)))
 
 
-def make_inputs(workload, M_override=None):
+def make_inputs(workload, M_override=None, tol_override=None, k_override=None):
     from mlff_preconditioner_b200 import synthetic
     from mlff_preconditioner_b200.desc import Desc, tril_perms_lin_from_perms
 
@@ -61,6 +61,10 @@ def make_inputs(workload, M_override=None):
     y /= y_std
     n = 3 * N * M
     k = min(rule_of_thumb(n, 10, 0.87), n // 4)  # ethanol parameters (plot_data.py:677-706)
+    if k_override:
+        k = k_override
+    if tol_override:
+        tol = tol_override
     task = {'R_train': ds['R'], 'F_train': ds['F'], 'sig': 10, 'lam': 1e-10, 'perms': perms, 'use_E_cstr': False,
             'solver_tol': tol, 'n_inducing_pts_init': 25, 'truncated_cholesky': 1500}
     return dict(kind=kind, M=M, N=N, n=n, k=k, tol=tol, task=task, R_desc=R_desc, R_d_desc=R_d_desc, tpl=tpl,
@@ -186,7 +190,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    inp = make_inputs(args.workload, args.M)
+    inp = make_inputs(args.workload, args.M, args.tol, args.k)
     consts = load_constants().get(args.workload, {})
     cg_iters = int(consts.get('cg_iters', 1000))
     src = 'bench_constants.json' if 'cg_iters' in consts else 'assumed (no GPU run recorded yet)'
@@ -247,7 +251,7 @@ def run_ours(args):
     from mlff_preconditioner_b200.solvers.iterative_solver import Iterative
 
     lib = _lib.load()
-    inp = make_inputs(args.workload, args.M)
+    inp = make_inputs(args.workload, args.M, args.tol, args.k)
     n, k = inp['n'], inp['k']
     frac = (k + 0.5) / n  # int(frac * n) == k
     task = dict(inp['task'])
@@ -270,7 +274,7 @@ def run_ours(args):
     eng = Engine(inp['R_desc'], inp['R_d_desc'], inp['tpl'], 10, perms=inp['perms'], rank=rank, world=world,
                  init_comm=init_engine_comm if world > 1 else None)
     y_t = torch.as_tensor(inp['y'], device=dev)
-    if args.mode == 'assembled':
+    if args.mode in ('assembled', 'assembled_sym'):
         task['_K_buffer'] = eng.empty(eng.n_local, eng.n)
     n_ind = min(inp['M'], int(max(np.ceil(frac * inp['M']), 1)))
     stats = []
@@ -313,10 +317,12 @@ def run_ours(args):
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
     avg_op_s = op_ms * 1e-3 / max(op_calls, 1)
-    if args.mode == 'assembled':
+    if args.mode in ('assembled', 'assembled_sym'):
         alg_bytes = 8.0 * eng.n_local * eng.n + 8.0 * eng.n + 8.0 * eng.n_local
         achieved = alg_bytes / avg_op_s / 1e9
-        roofline = {'bound': 'hbm', 'kernel': 'gemv_rows_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+        kname = 'gemv_rows_kernel' if (args.mode == 'assembled' or world > 1) else \
+            'symv_strip_kernel + symv_reduce_kernel (reads the lower triangle only: physical traffic ~ half the algorithmic bytes)'
+        roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                     'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
                     'bytes_per_launch': alg_bytes, 'avg_launch_ms': avg_op_s * 1e3, 'launches_timed': op_calls}
     else:
@@ -336,7 +342,8 @@ def run_ours(args):
     torch.cuda.empty_cache()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h2d = d2h = 0
-    for rep in range(1 + e2e_steps):  # one warm-up
+    res = None
+    for rep in range(0 if args.no_e2e else 1 + e2e_steps):  # one warm-up
         if rep == 1:
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -347,10 +354,13 @@ def run_ours(args):
         h2d, d2h = its.timings['h2d_bytes'], its.timings['d2h_bytes']
         its.engine.close()
         del its
-    e1.record()
-    barrier()
-    e2e_s = max_over_ranks(e0.elapsed_time(e1) * 1e-3) / e2e_steps
-    agree = float(np.linalg.norm(res[0] - alphas_dev) / np.linalg.norm(alphas_dev))
+    if res is not None:
+        e1.record()
+        barrier()
+        e2e_s = max_over_ranks(e0.elapsed_time(e1) * 1e-3) / e2e_steps
+        agree = float(np.linalg.norm(res[0] - alphas_dev) / np.linalg.norm(alphas_dev))
+    else:
+        e2e_s = agree = None
 
     line = {
         'metric': 'pcg_time_to_solution', 'value': value, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
@@ -393,9 +403,12 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--M', type=int, default=None, help='override the number of training points')
-    ap.add_argument('--mode', default='assembled', choices=['assembled', 'matrix_free'])
+    ap.add_argument('--mode', default='assembled', choices=['assembled', 'assembled_sym', 'matrix_free'])
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer arm (profiling runs)')
+    ap.add_argument('--tol', type=float, default=None, help='override the relative residual target (profiling runs)')
+    ap.add_argument('--k', type=int, default=None, help='override the preconditioner rank')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -86,6 +86,15 @@ int mlffpc_kernel_columns(mlffpc_ctx* ctx, const int64_t* cols, int64_t b, doubl
 int mlffpc_gemv(mlffpc_ctx* ctx, const double* K, int64_t n_rows, int64_t n_cols, int64_t ld,
                 const double* x, double* y, double alpha, double shift, int64_t x_off, void* stream);
 
+/* Symmetric assembled matvec (single GPU): y = alpha * K x + shift * x reading only the lower triangle of the
+ * symmetric K (by 32-row strips; each entry is used for y[r] and y[c]) -- about half the HBM traffic of
+ * mlffpc_gemv.  Deterministic (no atomics).  mlffpc_set_option(ctx, "symmetric_gemv", 1) makes mlffpc_pcg use
+ * it for the assembled operator. */
+int mlffpc_symv_workspace_bytes(int64_t n, int64_t* bytes);
+int mlffpc_symv(mlffpc_ctx* ctx, const double* K, int64_t n, int64_t ld, const double* x, double* y,
+                double alpha, double shift, void* workspace, int64_t workspace_bytes, void* stream);
+int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value);
+
 /* Matrix-free matvec  y_local = alpha * (K v)_local + shift * v_local, v is the full n-vector.
  * Replaces GDMLPredict.set_alphas + predict (predict.py:400-449, 997-1052) ->
  * GDMLTorchPredict.set_alphas/_forward (torchtools.py:128-151, 172-272), numpy twin

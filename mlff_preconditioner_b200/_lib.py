@@ -37,6 +37,9 @@ SIGNATURES = {
     'mlffpc_kernel_columns_workspace_bytes': [c_ptr, c_i64, ctypes.POINTER(c_i64)],
     'mlffpc_kernel_columns': [c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_dbl, c_ptr, c_i64, c_ptr],
     'mlffpc_gemv': [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_i64, c_ptr],
+    'mlffpc_symv_workspace_bytes': [c_i64, ctypes.POINTER(c_i64)],
+    'mlffpc_symv': [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_i64, c_ptr],
+    'mlffpc_set_option': [c_ptr, c_str, c_i64],
     'mlffpc_matvec_free_workspace_bytes': [c_ptr, ctypes.POINTER(c_i64)],
     'mlffpc_matvec_free': [c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_i64, c_ptr],
     'mlffpc_dgemm': [c_ptr, c_int, c_i64, c_i64, c_i64, c_dbl, c_ptr, c_i64, c_ptr, c_i64, c_dbl, c_ptr,

@@ -76,6 +76,7 @@ struct mlffpc_ctx {
     int64_t n_local() const { return (pt1 - pt0) * (int64_t)dim_i; }
     int64_t row0() const { return pt0 * (int64_t)dim_i; }
     mlffpc::Comm comm;
+    bool use_symv = false;  // option "symmetric_gemv": single-GPU assembled operator reads only the lower triangle
     // small persistent device scratch owned by the ctx (scalars / partial reductions, a few KB)
     double* scal = nullptr;    // device scalars
     double* h_scal = nullptr;  // pinned host mirror
@@ -122,6 +123,9 @@ int launch_gemv_rows(const double* K, int64_t n_rows, int64_t n_cols, int64_t ld
 int launch_tgemv_cols(const double* T, int64_t k, int64_t n_cols, int64_t ld, const double* w,
                       double* out, int post, const double* r, double sign_over_lam, int num_sms,
                       cudaStream_t s);
+int64_t symv_ws_bytes(int64_t n);
+int launch_symv(const double* K, int64_t n, int64_t ld, const double* x, double* y, double alpha, double shift,
+                void* workspace, cudaStream_t s);
 // one column of scale*K on the local rows, column index read from device memory (geometry.cu)
 int launch_columns_device_col(mlffpc_ctx* ctx, const int64_t* col_dev, double* out, double scale,
                               cudaStream_t s);

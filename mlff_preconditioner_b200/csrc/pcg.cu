@@ -89,7 +89,7 @@ static inline unsigned vec_grid(int64_t n) {
 }
 
 struct PcgWs {
-    int64_t n_pad, off_r, off_z, off_q, off_p, off_xg, off_u, off_mv, total;
+    int64_t n_pad, off_r, off_z, off_q, off_p, off_xg, off_u, off_mv, off_symv, total;
 };
 static PcgWs pcg_layout(const mlffpc_ctx* c, int64_t k, bool matrix_free) {
     auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
@@ -106,6 +106,7 @@ static PcgWs pcg_layout(const mlffpc_ctx* c, int64_t k, bool matrix_free) {
     w.off_xg = o; o = up(o + (world > 1 ? world * w.n_pad * 8 : 0));
     w.off_u = o; o = up(o + (k + 1) * 8);
     w.off_mv = o; o = up(o + (matrix_free ? matvec_free_ws_bytes(c) : 0));
+    w.off_symv = o; o = up(o + ((!matrix_free && c->use_symv && world == 1) ? symv_ws_bytes(c->n) : 0));
     w.total = o + 256;
     return w;
 }
@@ -116,8 +117,11 @@ struct PcgOp {
     int64_t ld_k;
     double lam;
     void* mv_ws;
+    void* symv_ws;
     // q_local = A v,  A = -K + lam I;  v_full is the replicated n-vector
     int apply(const double* v_full, double* q_local, cudaStream_t s) const {
+        if (K && ctx->use_symv && ctx->comm.world == 1)
+            return launch_symv(K, ctx->n, ld_k, v_full, q_local, -1.0, lam, symv_ws, s);
         if (K)
             return launch_gemv_rows(K, ctx->n_local(), ctx->n, ld_k, v_full, q_local, -1.0, lam, ctx->row0(), s);
         return matvec_free(ctx, v_full, q_local, -1.0, lam, mv_ws, s);
@@ -177,7 +181,7 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     double* p = p_full + row0;
     double* xg = (world > 1) ? (double*)(base + w.off_xg) : nullptr;
     double* u = (double*)(base + w.off_u);
-    PcgOp A{ctx, K_local, ld_k, lam, (void*)(base + w.off_mv)};
+    PcgOp A{ctx, K_local, ld_k, lam, (void*)(base + w.off_mv), (void*)(base + w.off_symv)};
     double* sc = ctx->scal;
     unsigned* counter = (unsigned*)(sc + S_COUNTER);
     const unsigned g = vec_grid(nl);

@@ -166,6 +166,22 @@ class Engine(object):
                                         float(alpha), float(shift), int(x_off), self._stream()))
         return out
 
+    def set_option(self, name, value):
+        _lib.check(self.lib.mlffpc_set_option(self.ctx, name.encode(), int(value)))
+
+    def symv(self, K, x, alpha=1.0, shift=0.0, out=None):
+        """alpha*K x + shift*x for a symmetric assembled K (single GPU); reads only the lower triangle."""
+        n = K.shape[0]
+        assert K.shape == (n, n) and K.stride(1) == 1 and x.is_contiguous() and x.numel() >= n
+        if out is None:
+            out = self.empty(n)
+        nb = ctypes.c_int64()
+        _lib.check(self.lib.mlffpc_symv_workspace_bytes(n, ctypes.byref(nb)))
+        ws = self._ws('symv', nb.value)
+        _lib.check(self.lib.mlffpc_symv(self.ctx, _ptr(K), n, K.stride(0), _ptr(x), _ptr(out), float(alpha),
+                                        float(shift), _ptr(ws), nb.value, self._stream()))
+        return out
+
     def matvec_free(self, v, alpha=1.0, shift=0.0, out=None):
         """alpha*(K v)_local + shift*v_local for the full n-vector v (predict.py:400-449,997-1052)."""
         assert v.numel() >= self.n and v.is_contiguous()

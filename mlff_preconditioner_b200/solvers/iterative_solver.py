@@ -130,8 +130,10 @@ class Iterative(object):
         'auto' = assembled when the row block fits next to the preconditioner, else matrix-free
         (BASELINE.json north_star)."""
         mode = task.get('kernel_mode', 'auto')
-        if mode not in ('auto', 'assembled', 'matrix_free'):
-            raise ValueError("task['kernel_mode'] must be 'auto', 'assembled' or 'matrix_free'")
+        if mode not in ('auto', 'assembled', 'assembled_sym', 'matrix_free'):
+            raise ValueError("task['kernel_mode'] must be 'auto', 'assembled', 'assembled_sym' or 'matrix_free'")
+        if mode == 'assembled_sym' and self.engine.world > 1:
+            mode = 'assembled'  # the symmetric matvec is single-GPU; row-block shards use the plain GEMV
         if mode != 'auto':
             return mode
         eng = self.engine
@@ -203,7 +205,8 @@ class Iterative(object):
         mode = self._choose_kernel_mode(task, k_rank)
         t0 = timeit.default_timer()
         self.K_local = None
-        if mode == 'assembled':
+        eng.set_option('symmetric_gemv', 1 if mode == 'assembled_sym' else 0)
+        if mode in ('assembled', 'assembled_sym'):
             self.K_local = eng.kernel_assemble(out=task.get('_K_buffer'))
         sync()
         self.timings['assemble'] = timeit.default_timer() - t0

@@ -1,0 +1,190 @@
+"""CPU, world_size = 2, gloo: the host side of the multi-GPU path.
+
+ * the row-block partition (engine.shard_points / dist.shard_slices) tiles the rows exactly;
+ * the NCCL-unique-id exchange (dist.broadcast_bytes) works through the default process group;
+ * the sharded algorithms -- the exact sequence of collectives libmlffpc issues (per pivot step: an
+   allgather of (value, position, index) candidates with first-position tie break + an allreduce-sum of the
+   zero-padded pivot row; per CG iteration: an allgather of p and three scalar + one k-vector allreduce) --
+   reproduce the single-process oracle when emulated with numpy shards over gloo.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import load_golden
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _allreduce(x):
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+    dist.all_reduce(t)
+    return t.numpy()
+
+
+def _allgather(x):
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, t)
+    return [o.numpy() for o in outs]
+
+
+def _sharded_pchol(A_rows, diag_local, row0, n, k):
+    """Pivoted Cholesky on a row shard: A_rows = A[row0:row0+nl, :]."""
+    nl = A_rows.shape[0]
+    index_columns = np.arange(n)
+    pos = np.arange(n)
+    Lt = np.zeros((k, nl))
+    diag = diag_local.copy()
+    for m in range(k):
+        cand = np.array([-1e300, 1e300, -1.0])
+        for r in range(nl):
+            g = row0 + r
+            if pos[g] >= m:
+                if diag[r] > cand[0] or (diag[r] == cand[0] and pos[g] < cand[1]):
+                    cand = np.array([diag[r], float(pos[g]), float(g)])
+        best = np.array([-1e300, 1e300, -1.0])
+        for c in _allgather(cand):
+            if c[0] > best[0] or (c[0] == best[0] and c[1] < best[1]):
+                best = c
+        pi = int(best[2])
+        i_argmax, e = pos[pi], index_columns[m]
+        index_columns[m], index_columns[i_argmax] = pi, e
+        pos[pi], pos[e] = m, i_argmax
+        lpiv = np.sqrt(best[0])
+        lrow = np.zeros(max(m, 1))
+        if row0 <= pi < row0 + nl and m > 0:
+            lrow[:m] = Lt[:m, pi - row0]
+        lrow = _allreduce(lrow)
+        col = A_rows[:, pi]
+        for r in range(nl):
+            g = row0 + r
+            if pos[g] > m:
+                l = (col[r] - Lt[:m, r] @ lrow[:m]) / lpiv
+                Lt[m, r] = l
+                diag[r] -= l * l
+            elif g == pi:
+                Lt[m, r] = lpiv
+    return Lt, index_columns
+
+
+def _sharded_pcg(A_rows, b_local, T_local, lam, row0, n, tol, maxiter):
+    nl = A_rows.shape[0]
+
+    def precon(r):
+        u = _allreduce(T_local @ r)
+        return (r - T_local.T @ u) / lam
+
+    def gather(v_local):
+        return np.concatenate(_allgather(v_local))  # equal shards in this test
+
+    x = np.zeros(nl)
+    bnrm2 = np.sqrt(_allreduce(np.array([b_local @ b_local]))[0])
+    r = b_local - A_rows @ gather(x)
+    atol = tol * bnrm2
+    rho_prev, p, it, info = None, None, 0, 1
+    while it < maxiter:
+        it += 1
+        z = precon(r)
+        rho = _allreduce(np.array([r @ z]))[0]
+        p = z.copy() if it == 1 else z + (rho / rho_prev) * p
+        q = A_rows @ gather(p)
+        alpha = rho / _allreduce(np.array([p @ q]))[0]
+        x += alpha * p
+        r -= alpha * q
+        rho_prev = rho
+        resid = np.sqrt(_allreduce(np.array([r @ r]))[0])
+        if resid <= atol and it > 1:
+            r = b_local - A_rows @ gather(x)
+            resid = np.sqrt(_allreduce(np.array([r @ r]))[0])
+        if resid <= atol:
+            info = 0
+            break
+    return x, it, info
+
+
+def _worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from mlff_preconditioner_b200.dist import broadcast_bytes, dist_info, shard_slices
+        from mlff_preconditioner_b200.engine import shard_points
+        from oracle import sgdml_oracle as orc
+
+        assert dist_info()[:2] == (rank, world)
+        ident = bytes(range(128)) if rank == 0 else bytes(128)
+        assert broadcast_bytes(ident, src=0) == bytes(range(128))
+
+        g = load_golden('eth_s1_m12')
+        M, dim_i = 12, 27
+        n = M * dim_i
+        pt0, pt1 = shard_points(M, rank, world)
+        row0, row1 = shard_slices(M, dim_i, world)[rank]
+        assert (row0, row1) == (pt0 * dim_i, pt1 * dim_i)
+        lam, k = float(g['lam']), int(g['chol_k'])
+        A = -g['K'] + lam * np.eye(n)
+        Lt, idx = _sharded_pchol(A[row0:row1], g['diag'][row0:row1], row0, n, k)
+        assert np.array_equal(idx, g['index_columns'])
+        assert np.abs(Lt.T - g['L'][row0:row1]).max() < 1e-12
+        # Woodbury factor from the reduced Gram, then the sharded PCG
+        W = _allreduce(Lt @ Lt.T) + lam * np.eye(k)
+        T_local = np.linalg.solve(np.linalg.cholesky(W), Lt)
+        x, iters, info = _sharded_pcg(A[row0:row1], g['y'][row0:row1], T_local, lam, row0, n, 1e-4, 5 * n)
+        L_full = g['L']
+        T_ref = orc.woodbury_factor(L_full, lam)
+        x_ref, it_ref, _, info_ref = orc.pcg(lambda v: A @ v, g['y'], lambda a: orc.woodbury_apply(T_ref, lam, a),
+                                             1e-4, 5 * n)
+        assert info == 0 and info_ref == 0
+        assert abs(iters - it_ref) <= max(1, int(0.05 * it_ref)), (iters, it_ref)
+        err = np.linalg.norm(x - x_ref[row0:row1]) / np.linalg.norm(x_ref[row0:row1])
+        assert err < 1e-3, err
+        q.put((rank, 'ok'))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, 'FAIL: %s\n%s' % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_covers_rows():
+    from mlff_preconditioner_b200.dist import shard_slices
+    from mlff_preconditioner_b200.engine import shard_points
+
+    for M, world in [(12, 2), (4000, 8), (10000, 8), (7, 3), (9, 4)]:
+        sl = shard_slices(M, 27, world)
+        assert sl[0][0] == 0 and max(s[1] for s in sl) == M * 27
+        for (a0, a1), (b0, b1) in zip(sl[:-1], sl[1:]):
+            assert a1 == b0 or b0 >= M * 27
+        ppr = -(-M // world)
+        for r in range(world):
+            if r * ppr < M:
+                assert shard_points(M, r, world) == (r * ppr, min((r + 1) * ppr, M))
+    with pytest.raises(ValueError):
+        shard_points(2, 3, 4)
+
+
+@pytest.mark.timeout(300)
+def test_world2_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == 'ok', 'rank %d: %s' % (rank, msg)

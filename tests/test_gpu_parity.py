@@ -62,6 +62,14 @@ def test_matvec_free_and_gemv(torch_cuda, golden, case):
     K = eng.kernel_assemble()
     out2 = eng.gemv(K, v, alpha=1.0, shift=-lam, x_off=0).cpu().numpy()
     assert relerr(out2, g['K_op_v']) < TOL
+    # symmetric matvec: only the lower triangle is read (poison the strict upper part to prove it)
+    Ksym = K.clone()
+    n = eng.n
+    iu = torch.triu_indices(n, n, offset=32, device=eng.device)
+    Ksym[iu[0], iu[1]] = float('nan')
+    out3 = eng.symv(Ksym, v, alpha=1.0, shift=-lam).cpu().numpy()
+    assert relerr(out3, g['K_op_v']) < TOL
+    assert np.array_equal(out3, eng.symv(Ksym, v, alpha=1.0, shift=-lam).cpu().numpy())  # deterministic
     from mlff_preconditioner_b200.solvers.operators import KernelOperator
     assert relerr(KernelOperator(eng, lam).matvec(g['v']), g['K_op_v']) < TOL
     assert relerr((-KernelOperator(eng, lam, K_local=K)).matvec(g['v']), -g['K_op_v']) < TOL
@@ -111,7 +119,7 @@ def _check_solve(g, s, frac):
     from mlff_preconditioner_b200.solvers.iterative_solver import Iterative
 
     out = {}
-    for mode in ('assembled', 'matrix_free'):
+    for mode in ('assembled', 'assembled_sym', 'matrix_free'):
         task = _task(g)
         task['kernel_mode'] = mode
         np.random.seed(0)
