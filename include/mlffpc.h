@@ -86,13 +86,32 @@ int mlffpc_kernel_columns(mlffpc_ctx* ctx, const int64_t* cols, int64_t b, doubl
 int mlffpc_gemv(mlffpc_ctx* ctx, const double* K, int64_t n_rows, int64_t n_cols, int64_t ld,
                 const double* x, double* y, double alpha, double shift, int64_t x_off, void* stream);
 
-/* Symmetric assembled matvec (single GPU): y = alpha * K x + shift * x reading only the lower triangle of the
- * symmetric K (by 32-row strips; each entry is used for y[r] and y[c]) -- about half the HBM traffic of
- * mlffpc_gemv.  Deterministic (no atomics).  mlffpc_set_option(ctx, "symmetric_gemv", 1) makes mlffpc_pcg use
- * it for the assembled operator. */
+/* Symmetric assembled matvec on one square: y = alpha * K x + shift * x reading only the lower triangle of
+ * the symmetric K (by 32-row strips; each entry is used for y[r] and y[c]) -- about half the HBM traffic of
+ * mlffpc_gemv.  Deterministic (no atomics). */
 int mlffpc_symv_workspace_bytes(int64_t n, int64_t* bytes);
 int mlffpc_symv(mlffpc_ctx* ctx, const double* K, int64_t n, int64_t ld, const double* x, double* y,
                 double alpha, double shift, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Symmetric tile operator (any number of ranks): the G x G grid of point blocks is dealt out so that each
+ * unordered block pair is stored on exactly one rank and every rank holds ~ n_local * n / 2 entries
+ * (rank g: the diagonal tile, tiles (g, g+d) for d < G/2 and half of tile (g, g+G/2) when G is even).
+ * One matvec reads every stored entry once (rows and columns of the product), then one reduce-scatter of n
+ * doubles combines the ranks.  Same result as mlffpc_gemv on the assembled row block up to summation order;
+ * half the HBM bytes and half the memory (n = 270 000 fits on 4 B200s).
+ *   storage_elems: doubles the caller allocates for Ksym (16-byte aligned)
+ *   tiles: 8 int64 per tile {i_pt0, i_pt1, j_pt0, j_pt1, ld, offset, is_diagonal, 0}  (out may be NULL to count)
+ *   assemble: fills Ksym from the geometry (replaces train.py:1121-1308 incl. its exploit_sym mirror, :207-210)
+ *   apply: y_local = alpha * (K x)_local + shift * x_local; with partial_out != NULL the rank's full-length
+ *          partial product (world * n_pad doubles) is written there instead and no collective is issued.
+ * mlffpc_set_option(ctx, "symmetric_gemv", 1) makes mlffpc_pcg treat K_local as this storage.
+ * Options "layout_world"/"layout_rank" override the partition taken from the communicator (rank emulation). */
+int mlffpc_symop_storage_elems(mlffpc_ctx* ctx, int64_t* elems);
+int mlffpc_symop_tiles(mlffpc_ctx* ctx, int64_t* out, int64_t max_tiles, int64_t* n_tiles);
+int mlffpc_symop_assemble(mlffpc_ctx* ctx, double* Ksym, void* stream);
+int mlffpc_symop_workspace_bytes(mlffpc_ctx* ctx, int64_t* bytes);
+int mlffpc_symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full, double* y_local, double alpha,
+                       double shift, void* workspace, int64_t workspace_bytes, double* partial_out, void* stream);
 int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value);
 
 /* Matrix-free matvec  y_local = alpha * (K v)_local + shift * v_local, v is the full n-vector.

@@ -40,6 +40,11 @@ SIGNATURES = {
     'mlffpc_symv_workspace_bytes': [c_i64, ctypes.POINTER(c_i64)],
     'mlffpc_symv': [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_i64, c_ptr],
     'mlffpc_set_option': [c_ptr, c_str, c_i64],
+    'mlffpc_symop_storage_elems': [c_ptr, ctypes.POINTER(c_i64)],
+    'mlffpc_symop_tiles': [c_ptr, c_ptr, c_i64, ctypes.POINTER(c_i64)],
+    'mlffpc_symop_assemble': [c_ptr, c_ptr, c_ptr],
+    'mlffpc_symop_workspace_bytes': [c_ptr, ctypes.POINTER(c_i64)],
+    'mlffpc_symop_apply': [c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_i64, c_ptr, c_ptr],
     'mlffpc_matvec_free_workspace_bytes': [c_ptr, ctypes.POINTER(c_i64)],
     'mlffpc_matvec_free': [c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_i64, c_ptr],
     'mlffpc_dgemm': [c_ptr, c_int, c_i64, c_i64, c_i64, c_dbl, c_ptr, c_i64, c_ptr, c_i64, c_dbl, c_ptr,

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmlffpc.so')
-SOURCES = ['core.cu', 'geometry.cu', 'matvec.cu', 'gemv.cu', 'dense.cu', 'pchol.cu', 'precon.cu', 'pcg.cu']
+SOURCES = ['core.cu', 'geometry.cu', 'matvec.cu', 'gemv.cu', 'symop.cu', 'dense.cu', 'pchol.cu', 'precon.cu', 'pcg.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default', '--use_fast_math=false']
 
@@ -18,12 +18,28 @@ def _nvcc():
     raise RuntimeError('nvcc not found')
 
 
+STAMP = LIB + '.stamp'
+
+
+def _source_digest():
+    """Content hash of every source the library is built from (mtimes do not survive the copy to a GPU box)."""
+    import hashlib
+
+    h = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h')))
+    deps.append(os.path.join(HERE, '..', 'include', 'mlffpc.h'))
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 'mlffpc.h')]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != _source_digest()
 
 
 def build(force=False, verbose=False):
@@ -49,7 +65,9 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')
-    subprocess.check_call([nvcc, '-shared', '-o', LIB] + objs + ['-ldl'])
+    subprocess.check_call([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs + ['-ldl'])
+    with open(STAMP, 'w') as f:
+        f.write(_source_digest())
     return LIB
 
 

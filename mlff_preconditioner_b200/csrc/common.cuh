@@ -14,6 +14,17 @@ void set_error(const char* fmt, ...);
 extern long long g_launches;  // kernels launched by this library (bench.py's gpu_launches)
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
+// Profiler windows (ncu --profile-from-start off): the environment variable MLFFPC_PROFILE holds
+// "<phase>:<first>:<count>[,<phase>:...]" with phase in {pcg, pchol, woodbury, syrk, potrf, trsm, assemble}; the library brackets
+// iterations/steps [first, first+count) of that phase with cudaProfilerStart/Stop.  Unset = no effect.
+struct ProfWindow {
+    long long first = -1, count = 0;
+    bool active = false;
+    void step(long long i);  // call at the start of iteration/step i
+    void end();              // call when the phase ends
+};
+ProfWindow prof_window(const char* phase);
+
 #define MLFFPC_CUDA(call)                                                          \
     do {                                                                           \
         cudaError_t _e = (call);                                                   \
@@ -51,6 +62,7 @@ struct Comm {
 int comm_allreduce_sum(Comm& c, double* buf, size_t count, cudaStream_t s);
 int comm_allgather(Comm& c, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s);
 int comm_broadcast(Comm& c, void* buf, size_t bytes, int root, cudaStream_t s);
+int comm_reduce_scatter_sum(Comm& c, const double* send, double* recv, size_t count_per_rank, cudaStream_t s);
 
 }  // namespace mlffpc
 
@@ -76,7 +88,10 @@ struct mlffpc_ctx {
     int64_t n_local() const { return (pt1 - pt0) * (int64_t)dim_i; }
     int64_t row0() const { return pt0 * (int64_t)dim_i; }
     mlffpc::Comm comm;
-    bool use_symv = false;  // option "symmetric_gemv": single-GPU assembled operator reads only the lower triangle
+    // partition used by the symmetric tile operator; follows the communicator unless overridden by the
+    // options "layout_rank"/"layout_world" (rank emulation on one GPU, tests only)
+    int lay_rank = 0, lay_world = 1;
+    bool use_symv = false;  // option "symmetric_gemv": the assembled operator is the symmetric tile storage (symop.cu)
     // small persistent device scratch owned by the ctx (scalars / partial reductions, a few KB)
     double* scal = nullptr;    // device scalars
     double* h_scal = nullptr;  // pinned host mirror
@@ -123,9 +138,18 @@ int launch_gemv_rows(const double* K, int64_t n_rows, int64_t n_cols, int64_t ld
 int launch_tgemv_cols(const double* T, int64_t k, int64_t n_cols, int64_t ld, const double* w,
                       double* out, int post, const double* r, double sign_over_lam, int num_sms,
                       cudaStream_t s);
+// symmetric operator (symop.cu)
 int64_t symv_ws_bytes(int64_t n);
 int launch_symv(const double* K, int64_t n, int64_t ld, const double* x, double* y, double alpha, double shift,
                 void* workspace, cudaStream_t s);
+int64_t symop_storage_elems(const mlffpc_ctx* ctx);
+int64_t symop_ws_bytes(const mlffpc_ctx* ctx);
+int symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full, double* y_local, double alpha,
+                double shift, void* workspace, double* partial_out, cudaStream_t s);
+// explicit rectangle K[points i_pt0:i_pt1, points j_pt0:j_pt1] -> out (row-major, ld); diag_tr >= 0 skips the
+// point blocks right of the diagonal that a lower-triangle reader with diag_tr-row strips never touches
+int assemble_tile(mlffpc_ctx* ctx, int64_t i_pt0, int64_t i_pt1, int64_t j_pt0, int64_t j_pt1, double* out,
+                  int64_t ld, int diag_tr, cudaStream_t s);
 // one column of scale*K on the local rows, column index read from device memory (geometry.cu)
 int launch_columns_device_col(mlffpc_ctx* ctx, const int64_t* col_dev, double* out, double scale,
                               cudaStream_t s);

@@ -1,5 +1,7 @@
 // Context lifecycle, error plumbing, NCCL binding (dlopen).
+#include <cuda_profiler_api.h>
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -22,6 +24,31 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return MLFFPC_ERR_CUDA;
 }
 
+ProfWindow prof_window(const char* phase) {
+    ProfWindow w;
+    const char* env = getenv("MLFFPC_PROFILE");
+    if (!env) return w;
+    const size_t pl = strlen(phase);
+    for (const char* p = env; p && *p;) {
+        if (strncmp(p, phase, pl) == 0 && p[pl] == ':') {
+            long long a = 0, b = 1;
+            if (sscanf(p + pl + 1, "%lld:%lld", &a, &b) >= 1) { w.first = a; w.count = b; }
+            break;
+        }
+        p = strchr(p, ',');
+        if (p) ++p;
+    }
+    return w;
+}
+void ProfWindow::step(long long i) {
+    if (first < 0) return;
+    if (!active && i == first) { cudaDeviceSynchronize(); cudaProfilerStart(); active = true; }
+    else if (active && i >= first + count) end();
+}
+void ProfWindow::end() {
+    if (active) { cudaDeviceSynchronize(); cudaProfilerStop(); active = false; }
+}
+
 // ------------------------------------------------------------------ NCCL via dlopen
 typedef int (*nccl_get_unique_id_t)(void*);
 struct NcclId {
@@ -31,6 +58,7 @@ typedef int (*nccl_comm_init_rank_fn)(void**, int, NcclId, int);
 typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*nccl_bcast_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_reduce_scatter_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*nccl_destroy_fn)(void*);
 typedef const char* (*nccl_errstr_fn)(int);
 
@@ -41,6 +69,7 @@ struct NcclApi {
     nccl_allreduce_fn allreduce = nullptr;
     nccl_allgather_fn allgather = nullptr;
     nccl_bcast_fn bcast = nullptr;
+    nccl_reduce_scatter_fn reduce_scatter = nullptr;
     nccl_destroy_fn destroy = nullptr;
     nccl_errstr_fn errstr = nullptr;
 };
@@ -58,10 +87,11 @@ static int nccl_load(const char* path) {
     g_nccl.allreduce = (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce");
     g_nccl.allgather = (nccl_allgather_fn)dlsym(lib, "ncclAllGather");
     g_nccl.bcast = (nccl_bcast_fn)dlsym(lib, "ncclBroadcast");
+    g_nccl.reduce_scatter = (nccl_reduce_scatter_fn)dlsym(lib, "ncclReduceScatter");
     g_nccl.destroy = (nccl_destroy_fn)dlsym(lib, "ncclCommDestroy");
     g_nccl.errstr = (nccl_errstr_fn)dlsym(lib, "ncclGetErrorString");
     if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.allreduce || !g_nccl.allgather ||
-        !g_nccl.bcast || !g_nccl.destroy) {
+        !g_nccl.bcast || !g_nccl.destroy || !g_nccl.reduce_scatter) {
         set_error("libnccl is missing a required symbol");
         return MLFFPC_ERR_COMM;
     }
@@ -89,6 +119,14 @@ int comm_allgather(Comm& c, const void* send, void* recv, size_t bytes_per_rank,
         return MLFFPC_OK;
     }
     return nccl_check(g_nccl.allgather(send, recv, bytes_per_rank, 0, c.comm, s), "ncclAllGather");
+}
+int comm_reduce_scatter_sum(Comm& c, const double* send, double* recv, size_t count_per_rank, cudaStream_t s) {
+    if (c.world <= 1) {
+        cudaError_t e = cudaMemcpyAsync(recv, send, count_per_rank * 8, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return cuda_fail(e, "reduce_scatter self copy", __FILE__, __LINE__);
+        return MLFFPC_OK;
+    }
+    return nccl_check(g_nccl.reduce_scatter(send, recv, count_per_rank, 8, 0, c.comm, s), "ncclReduceScatter");
 }
 int comm_broadcast(Comm& c, void* buf, size_t bytes, int root, cudaStream_t s) {
     if (c.world <= 1 || bytes == 0) return MLFFPC_OK;
@@ -149,12 +187,33 @@ int mlffpc_comm_init(mlffpc_ctx* ctx, const char* libnccl_path, const void* id12
     MLFFPC_REQUIRE(world >= 1 && rank >= 0 && rank < world, "comm_init: bad rank %d / world %d", rank, world);
     ctx->comm.rank = rank;
     ctx->comm.world = world;
+    ctx->lay_rank = rank;
+    ctx->lay_world = world;
     if (world == 1) return MLFFPC_OK;
     MLFFPC_TRY(nccl_load(libnccl_path));
     MLFFPC_CUDA(cudaSetDevice(ctx->device));
     NcclId id;
     memcpy(id.internal, id128, 128);
     return nccl_check(g_nccl.comm_init_rank(&ctx->comm.comm, world, id, rank), "ncclCommInitRank");
+}
+
+int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value) {
+    MLFFPC_REQUIRE(ctx && name, "set_option: NULL argument");
+    const std::string nm(name);
+    if (nm == "symmetric_gemv") { ctx->use_symv = value != 0; return MLFFPC_OK; }
+    if (nm == "layout_world") {
+        MLFFPC_REQUIRE(value >= 1 && value <= 1024, "set_option: layout_world out of range");
+        ctx->lay_world = (int)value;
+        if (ctx->lay_rank >= ctx->lay_world) ctx->lay_rank = 0;
+        return MLFFPC_OK;
+    }
+    if (nm == "layout_rank") {
+        MLFFPC_REQUIRE(value >= 0 && value < ctx->lay_world, "set_option: layout_rank out of range");
+        ctx->lay_rank = (int)value;
+        return MLFFPC_OK;
+    }
+    set_error("set_option: unknown option '%s'", name);
+    return MLFFPC_ERR_INVALID;
 }
 
 int mlffpc_allreduce_sum(mlffpc_ctx* ctx, double* buf, int64_t count, void* stream) {

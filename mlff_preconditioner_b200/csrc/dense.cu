@@ -261,6 +261,7 @@ __global__ void zero_upper_kernel(double* W, int64_t m, int64_t ldw) {
 
 // ---- blocked row-TRSM: X <- Lf^{-1} X, X[m, n_cols] row-major ------------------------------------
 constexpr int TRSM_NB = 32;
+constexpr int TRSM_OB = 256;
 
 // diagonal solve for block rows [j0, j0+nb): one thread per column of X
 __global__ void trsm_diag_kernel(const double* __restrict__ Lf, int64_t ldl, int64_t j0, int nb, double* X,
@@ -308,7 +309,11 @@ int mlffpc_syrk_rows(mlffpc_ctx* ctx, const double* X, int64_t m, int64_t n_cols
                      double shift, double* W, int64_t ldw, void* stream) {
     MLFFPC_REQUIRE(ctx && X && W && m > 0 && n_cols >= 0 && ldx >= n_cols && ldw >= m, "syrk_rows: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
-    MLFFPC_TRY(dgemm(true, m, m, n_cols, 1.0, X, ldx, X, ldx, 0.0, W, ldw, true, s));
+    ProfWindow pw = prof_window("syrk");
+    pw.step(pw.first);
+    const int st_gemm = dgemm(true, m, m, n_cols, 1.0, X, ldx, X, ldx, 0.0, W, ldw, true, s);
+    pw.end();
+    MLFFPC_TRY(st_gemm);
     if (ctx->comm.world > 1) {
         // the lower tiles of every rank are summed; entries above the diagonal tiles are rebuilt below
         MLFFPC_REQUIRE(ldw == m, "syrk_rows: multi-GPU reduction needs a packed W (ldw == m)");
@@ -326,7 +331,9 @@ int mlffpc_potrf_lower(mlffpc_ctx* ctx, double* W, int64_t m, int64_t ldw, int* 
     cudaStream_t s = (cudaStream_t)stream;
     int* d_info = (int*)(ctx->scal + MLFFPC_NUM_SCAL - 2);
     MLFFPC_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), s));
+    ProfWindow pw = prof_window("potrf");
     for (int64_t j0 = 0; j0 < m; j0 += POTRF_NB) {
+        pw.step(j0 / POTRF_NB);
         const int nb = (int)((m - j0 < POTRF_NB) ? (m - j0) : POTRF_NB);
         potrf_diag_kernel<<<1, 256, 0, s>>>(W, ldw, j0, nb, d_info);
         MLFFPC_LAUNCH_CHECK();
@@ -340,6 +347,7 @@ int mlffpc_potrf_lower(mlffpc_ctx* ctx, double* W, int64_t m, int64_t ldw, int* 
             MLFFPC_TRY(dgemm(true, rest, rest, nb, -1.0, L21, ldw, L21, ldw, 1.0, A22, ldw, true, s));
         }
     }
+    pw.end();
     zero_upper_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)m), 256, 0, s>>>(W, m, ldw);
     MLFFPC_LAUNCH_CHECK();
     int* h_info = (int*)(ctx->h_scal + MLFFPC_NUM_SCAL - 2);
@@ -354,17 +362,32 @@ int mlffpc_trsm_rows(mlffpc_ctx* ctx, const double* Lf, int64_t m, int64_t ldl, 
     MLFFPC_REQUIRE(ctx && Lf && X && m > 0 && ldl >= m && n_cols >= 0 && ldx >= n_cols, "trsm_rows: bad argument");
     if (n_cols == 0) return MLFFPC_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    for (int64_t j0 = 0; j0 < m; j0 += TRSM_NB) {
-        const int nb = (int)((m - j0 < TRSM_NB) ? (m - j0) : TRSM_NB);
-        trsm_diag_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, s>>>(Lf, ldl, j0, nb, X, n_cols, ldx);
-        MLFFPC_LAUNCH_CHECK();
-        const int64_t rest = m - j0 - nb;
-        if (rest > 0) {
-            // X[j0+nb:, :] -= Lf[j0+nb:, j0:j0+nb] X[j0:j0+nb, :]
-            MLFFPC_TRY(dgemm(false, rest, n_cols, nb, -1.0, Lf + (j0 + nb) * ldl + j0, ldl, X + j0 * ldx, ldx,
-                             1.0, X + (j0 + nb) * ldx, ldx, false, s));
+    // Two-level blocking: inside an outer panel of TRSM_OB rows the 32-row diagonal solves update only the
+    // rest of that panel (K = 32 GEMMs over <= TRSM_OB rows); everything below the panel is updated once
+    // with a K = TRSM_OB GEMM, which is DMMA-bound instead of streaming all remaining rows 8 times.
+    ProfWindow pw = prof_window("trsm");
+    for (int64_t J0 = 0; J0 < m; J0 += TRSM_OB) {
+        pw.step(J0 / TRSM_OB);
+        const int64_t J1 = (J0 + TRSM_OB < m) ? (J0 + TRSM_OB) : m;
+        for (int64_t j0 = J0; j0 < J1; j0 += TRSM_NB) {
+            const int nb = (int)((J1 - j0 < TRSM_NB) ? (J1 - j0) : TRSM_NB);
+            trsm_diag_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, s>>>(Lf, ldl, j0, nb, X, n_cols, ldx);
+            MLFFPC_LAUNCH_CHECK();
+            const int64_t rest = J1 - j0 - nb;
+            if (rest > 0) {
+                // X[j0+nb:J1, :] -= Lf[j0+nb:J1, j0:j0+nb] X[j0:j0+nb, :]
+                MLFFPC_TRY(dgemm(false, rest, n_cols, nb, -1.0, Lf + (j0 + nb) * ldl + j0, ldl, X + j0 * ldx, ldx,
+                                 1.0, X + (j0 + nb) * ldx, ldx, false, s));
+            }
+        }
+        const int64_t below = m - J1;
+        if (below > 0) {
+            // X[J1:, :] -= Lf[J1:, J0:J1] X[J0:J1, :]
+            MLFFPC_TRY(dgemm(false, below, n_cols, J1 - J0, -1.0, Lf + J1 * ldl + J0, ldl, X + J0 * ldx, ldx, 1.0,
+                             X + J1 * ldx, ldx, false, s));
         }
     }
+    pw.end();
     return MLFFPC_OK;
 }
 

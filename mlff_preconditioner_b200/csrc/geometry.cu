@@ -157,8 +157,8 @@ __device__ __forceinline__ double jtj_entry(const GeoView& g, const double* gi, 
 // ---- explicit block (i, j): one CTA -----------------------------------------------------
 // dynamic smem: ab[2S] | red[33] | u_i[S*dim_i] | u_j[S*dim_i]
 template <bool DIAG_ONLY>
-__global__ void assemble_block_kernel(GeoView g, int64_t pt0, int64_t M, double* __restrict__ out,
-                                      int64_t ld) {
+__global__ void assemble_block_kernel(GeoView g, int64_t pt0, int64_t j_pt0, int diag_tr,
+                                      double* __restrict__ out, int64_t ld) {
     extern __shared__ double sm[];
     double* sm_ab = sm;
     double* sm_red = sm_ab + 2 * g.S;
@@ -167,7 +167,9 @@ __global__ void assemble_block_kernel(GeoView g, int64_t pt0, int64_t M, double*
 
     const int64_t il = blockIdx.x;       // local row point
     const int64_t i = pt0 + il;
-    const int64_t j = DIAG_ONLY ? i : (int64_t)blockIdx.y;
+    const int64_t jl = DIAG_ONLY ? il : (int64_t)blockIdx.y;
+    const int64_t j = DIAG_ONLY ? i : j_pt0 + jl;
+    if (!DIAG_ONLY && diag_tr >= 0 && (j - i - 1) * g.dim_i >= diag_tr) return;  // never read by the strip reader
     const double* xi = g.R_desc + i * g.D;
     const double* gi = g.R_d_desc + i * g.D * 3;
     const double* gj = g.R_d_desc + j * g.D * 3;
@@ -194,7 +196,7 @@ __global__ void assemble_block_kernel(GeoView g, int64_t pt0, int64_t M, double*
         }
     } else {
         const int nent = g.dim_i * g.dim_i;
-        double* blk = out + (il * g.dim_i) * ld + j * g.dim_i;
+        double* blk = out + (il * g.dim_i) * ld + jl * g.dim_i;
         for (int t = threadIdx.x; t < nent; t += blockDim.x) {
             const int r = t / g.dim_i, r2 = t % g.dim_i;
             double val = 0.0;
@@ -330,7 +332,7 @@ int mlffpc_kernel_diag(mlffpc_ctx* ctx, double* out, void* stream) {
     MLFFPC_CUDA(cudaFuncSetAttribute(assemble_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int block = pick_block(g.D < g.dim_i ? g.dim_i : g.D);
     assemble_block_kernel<true><<<dim3((unsigned)(ctx->pt1 - ctx->pt0)), block, smem, (cudaStream_t)stream>>>(
-        g, ctx->pt0, ctx->M, out, 0);
+        g, ctx->pt0, 0, -1, out, 0);
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;
 }
@@ -338,16 +340,11 @@ int mlffpc_kernel_diag(mlffpc_ctx* ctx, double* out, void* stream) {
 int mlffpc_kernel_assemble(mlffpc_ctx* ctx, double* K_out, int64_t ld, void* stream) {
     MLFFPC_REQUIRE(ctx && K_out && ctx->M > 0, "kernel_assemble: geometry not set or NULL output");
     MLFFPC_REQUIRE(ld >= ctx->n, "kernel_assemble: ld %lld < n %lld", (long long)ld, (long long)ctx->n);
-    MLFFPC_REQUIRE(ctx->M <= 65535, "kernel_assemble: M > 65535 column points not supported by this launch shape");
-    GeoView g = make_view(ctx);
-    const size_t smem = (size_t)(2 * g.S + 40 + 2 * g.S * g.dim_i) * sizeof(double);
-    MLFFPC_REQUIRE(smem <= 200 * 1024, "kernel_assemble: S*3N = %d too large for shared memory", g.S * g.dim_i);
-    MLFFPC_CUDA(cudaFuncSetAttribute(assemble_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int block = pick_block(g.dim_i * g.dim_i);
-    assemble_block_kernel<false><<<dim3((unsigned)(ctx->pt1 - ctx->pt0), (unsigned)ctx->M), block, smem,
-                                   (cudaStream_t)stream>>>(g, ctx->pt0, ctx->M, K_out, ld);
-    MLFFPC_LAUNCH_CHECK();
-    return MLFFPC_OK;
+    ProfWindow pw = prof_window("assemble");
+    pw.step(pw.first);
+    const int st = assemble_tile(ctx, ctx->pt0, ctx->pt1, 0, ctx->M, K_out, ld, -1, (cudaStream_t)stream);
+    pw.end();
+    return st;
 }
 
 int mlffpc_kernel_columns_workspace_bytes(mlffpc_ctx* ctx, int64_t b, int64_t* bytes) {
@@ -381,6 +378,25 @@ int mlffpc_kernel_columns(mlffpc_ctx* ctx, const int64_t* cols, int64_t b, doubl
 }  // extern "C"
 
 namespace mlffpc {
+int assemble_tile(mlffpc_ctx* ctx, int64_t i_pt0, int64_t i_pt1, int64_t j_pt0, int64_t j_pt1, double* out,
+                  int64_t ld, int diag_tr, cudaStream_t s) {
+    MLFFPC_REQUIRE(0 <= i_pt0 && i_pt0 < i_pt1 && i_pt1 <= ctx->M && 0 <= j_pt0 && j_pt0 < j_pt1 && j_pt1 <= ctx->M,
+                   "assemble_tile: bad point ranges");
+    MLFFPC_REQUIRE(ld >= (j_pt1 - j_pt0) * ctx->dim_i, "assemble_tile: ld too small");
+    GeoView g = make_view(ctx);
+    const size_t smem = (size_t)(2 * g.S + 40 + 2 * g.S * g.dim_i) * sizeof(double);
+    MLFFPC_REQUIRE(smem <= 200 * 1024, "kernel_assemble: S*3N = %d too large for shared memory", g.S * g.dim_i);
+    MLFFPC_CUDA(cudaFuncSetAttribute(assemble_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int block = pick_block(g.dim_i * g.dim_i);
+    for (int64_t j0 = j_pt0; j0 < j_pt1; j0 += 65535) {  // grid.y limit
+        const int64_t nj = (j_pt1 - j0 < 65535) ? (j_pt1 - j0) : 65535;
+        assemble_block_kernel<false><<<dim3((unsigned)(i_pt1 - i_pt0), (unsigned)nj), block, smem, s>>>(
+            g, i_pt0, j0, diag_tr, out + (j0 - j_pt0) * g.dim_i, ld);
+        MLFFPC_LAUNCH_CHECK();
+    }
+    return MLFFPC_OK;
+}
+
 int launch_columns_device_col(mlffpc_ctx* ctx, const int64_t* col_dev, double* out, double scale,
                               cudaStream_t s) {
     return mlffpc_kernel_columns(ctx, col_dev, 1, out, ctx->n_local(), scale, nullptr, 0, (void*)s);

@@ -106,7 +106,7 @@ static PcgWs pcg_layout(const mlffpc_ctx* c, int64_t k, bool matrix_free) {
     w.off_xg = o; o = up(o + (world > 1 ? world * w.n_pad * 8 : 0));
     w.off_u = o; o = up(o + (k + 1) * 8);
     w.off_mv = o; o = up(o + (matrix_free ? matvec_free_ws_bytes(c) : 0));
-    w.off_symv = o; o = up(o + ((!matrix_free && c->use_symv && world == 1) ? symv_ws_bytes(c->n) : 0));
+    w.off_symv = o; o = up(o + ((!matrix_free && c->use_symv) ? symop_ws_bytes(c) : 0));
     w.total = o + 256;
     return w;
 }
@@ -120,8 +120,8 @@ struct PcgOp {
     void* symv_ws;
     // q_local = A v,  A = -K + lam I;  v_full is the replicated n-vector
     int apply(const double* v_full, double* q_local, cudaStream_t s) const {
-        if (K && ctx->use_symv && ctx->comm.world == 1)
-            return launch_symv(K, ctx->n, ld_k, v_full, q_local, -1.0, lam, symv_ws, s);
+        if (K && ctx->use_symv)  // K is the symmetric tile storage of this rank (symop.cu)
+            return symop_apply(ctx, K, v_full, q_local, -1.0, lam, symv_ws, nullptr, s);
         if (K)
             return launch_gemv_rows(K, ctx->n_local(), ctx->n, ld_k, v_full, q_local, -1.0, lam, ctx->row0(), s);
         return matvec_free(ctx, v_full, q_local, -1.0, lam, mv_ws, s);
@@ -160,7 +160,8 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     MLFFPC_REQUIRE(ctx && ctx->M > 0, "pcg: geometry not set");
     MLFFPC_REQUIRE(b && x && out_host && workspace, "pcg: NULL argument");
     MLFFPC_REQUIRE(lam > 0.0 && tol > 0.0 && maxiter >= 0, "pcg: bad lam/tol/maxiter");
-    MLFFPC_REQUIRE(!K_local || ld_k >= ctx->n, "pcg: ld_k < n");
+    MLFFPC_REQUIRE(!K_local || ctx->use_symv || ld_k >= ctx->n, "pcg: ld_k < n");
+    MLFFPC_REQUIRE(!ctx->use_symv || ctx->lay_world == ctx->comm.world, "pcg: symmetric tile layout does not match the communicator");
     MLFFPC_REQUIRE(!T || (k > 0 && ld_t >= ctx->n_local()), "pcg: bad preconditioner dimensions");
     const bool matrix_free = (K_local == nullptr);
     const PcgWs w = pcg_layout(ctx, T ? k : 0, matrix_free);
@@ -237,8 +238,10 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     int64_t it = 0;
     int info = (int)(maxiter > 0x7fffffff ? 0x7fffffff : maxiter);
     if (info == 0) info = 1;
+    ProfWindow pw = prof_window("pcg");
     while (it < maxiter) {
         ++it;
+        pw.step(it);
         double* rho = sc + (it & 1);
         double* rho_prev = sc + ((it - 1) & 1);
         // z = P r
@@ -286,6 +289,7 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
             break;
         }
     }
+    pw.end();
     for (auto& e : ev) cudaEventDestroy(e);
     out_host[0] = (double)it;
     out_host[1] = resid;

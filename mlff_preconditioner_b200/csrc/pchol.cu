@@ -256,7 +256,9 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
 
     int status = MLFFPC_OK;
     int prev_parts = 0;
+    ProfWindow pw = prof_window("pchol");
     for (int64_t m = 0; m < k && status == MLFFPC_OK; ++m) {
+        pw.step(m);
         // (1) candidates -> this rank's best
         if (m == 0) {
             MLFFPC_REQUIRE(n_part <= MLFFPC_MAX_PARTIALS, "pchol_build: n_local too large (%lld rows)", (long long)nl);
@@ -309,6 +311,7 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
         if (step_ms_host) cudaEventRecord(ev[(size_t)m + 1], s);
     }
 
+    pw.end();
     int h_flag = 0;
     if (status == MLFFPC_OK) {
         cudaError_t e = cudaMemcpyAsync(ctx->h_scal, flag, sizeof(int), cudaMemcpyDeviceToHost, s);

@@ -33,14 +33,18 @@ int mlffpc_woodbury_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, d
                            void* stream) {
     MLFFPC_REQUIRE(ctx && ctx->M > 0, "woodbury_factor: geometry not set");
     MLFFPC_REQUIRE(Lt && W && k > 0 && ld >= ctx->n_local(), "woodbury_factor: bad argument");
-    MLFFPC_TRY(mlffpc_syrk_rows(ctx, Lt, k, ctx->n_local(), ld, lam, W, k, stream));
+    ProfWindow pw = prof_window("woodbury");
+    pw.step(pw.first);
+    int st = mlffpc_syrk_rows(ctx, Lt, k, ctx->n_local(), ld, lam, W, k, stream);
     int info = 0;
-    MLFFPC_TRY(mlffpc_potrf_lower(ctx, W, k, k, &info, stream));
-    if (info != 0) {
+    if (st == MLFFPC_OK) st = mlffpc_potrf_lower(ctx, W, k, k, &info, stream);
+    if (st == MLFFPC_OK && info != 0) {
         set_error("%d-th leading minor of the array is not positive definite", info);
-        return MLFFPC_ERR_LINALG;
+        st = MLFFPC_ERR_LINALG;
     }
-    return mlffpc_trsm_rows(ctx, W, k, k, Lt, ctx->n_local(), ld, stream);
+    if (st == MLFFPC_OK) st = mlffpc_trsm_rows(ctx, W, k, k, Lt, ctx->n_local(), ld, stream);
+    pw.end();
+    return st;
 }
 
 int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,

@@ -70,3 +70,48 @@ def shard_slices(M, dim_i, world):
         pt0, pt1 = r * ppr, min((r + 1) * ppr, M)
         out.append((pt0 * dim_i, max(pt0, pt1) * dim_i))
     return out
+
+
+def symop_plan(M, world, rank):
+    """Host mirror of the symmetric tile plan in csrc/symop.cu: [(i_pt0, i_pt1, j_pt0, j_pt1, is_diag)] for
+    ``rank``.  Every unordered pair of point blocks is covered by exactly one rank and every rank reads
+    about half of its row block (tests/test_dist_gloo.py checks both properties)."""
+    ppr = (M + world - 1) // world
+
+    def blk(b):
+        return min(b * ppr, M), min((b + 1) * ppr, M)
+
+    tiles = []
+
+    def add(i0, i1, j0, j1, diag):
+        if i1 > i0 and j1 > j0:
+            tiles.append((i0, i1, j0, j1, diag))
+
+    g = rank
+    g0, g1 = blk(g)
+    add(g0, g1, g0, g1, 1)
+    for d in range(1, (world - 1) // 2 + 1):
+        h0, h1 = blk((g + d) % world)
+        add(g0, g1, h0, h1, 0)
+    if world > 1 and world % 2 == 0:
+        h0, h1 = blk((g + world // 2) % world)
+        if g < world // 2:
+            add(g0, g0 + (g1 - g0 + 1) // 2, h0, h1, 0)
+        else:
+            add(g0, g1, h0 + (h1 - h0 + 1) // 2, h1, 0)
+    return tiles
+
+
+def symop_entries_read(tiles, dim_i, strip_rows=32):
+    """Matrix entries one symmetric matvec reads from HBM for these tiles (diagonal tiles: the lower
+    triangle by ``strip_rows``-row strips including the diagonal blocks; other tiles: everything)."""
+    total = 0
+    for (i0, i1, j0, j1, diag) in tiles:
+        nr, nc = (i1 - i0) * dim_i, (j1 - j0) * dim_i
+        if not diag:
+            total += nr * nc
+            continue
+        for r0 in range(0, nr, strip_rows):
+            rows = min(strip_rows, nr - r0)
+            total += rows * (r0 + rows)
+    return total

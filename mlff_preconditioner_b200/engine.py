@@ -182,6 +182,58 @@ class Engine(object):
                                         float(shift), _ptr(ws), nb.value, self._stream()))
         return out
 
+    # ---- symmetric tile operator (half the bytes, any number of ranks) ------------------------
+    def set_layout(self, rank, world):
+        """Override the tile partition (rank emulation on one GPU; tests only)."""
+        self.set_option('layout_world', world)
+        self.set_option('layout_rank', rank)
+        self._lay_world = world
+
+    def symop_tiles(self):
+        """[(i_pt0, i_pt1, j_pt0, j_pt1, ld, offset, is_diag)] of this rank's tiles."""
+        nt = ctypes.c_int64()
+        _lib.check(self.lib.mlffpc_symop_tiles(self.ctx, ctypes.c_void_p(0), 0, ctypes.byref(nt)))
+        buf = (ctypes.c_int64 * (8 * nt.value))()
+        _lib.check(self.lib.mlffpc_symop_tiles(self.ctx, buf, nt.value, ctypes.byref(nt)))
+        return [tuple(buf[8 * i + j] for j in range(7)) for i in range(nt.value)]
+
+    def symop_storage_elems(self):
+        ne = ctypes.c_int64()
+        _lib.check(self.lib.mlffpc_symop_storage_elems(self.ctx, ctypes.byref(ne)))
+        return ne.value
+
+    def symop_assemble(self, out=None):
+        """This rank's tiles of the symmetric storage (a flat fp64 tensor)."""
+        ne = self.symop_storage_elems()
+        if out is None:
+            out = self.empty(ne)
+        assert out.is_contiguous() and out.numel() >= ne
+        _lib.check(self.lib.mlffpc_symop_assemble(self.ctx, _ptr(out), self._stream()))
+        return out
+
+    def symop_apply(self, Ksym, x_full, alpha=1.0, shift=0.0, out=None, partial=False):
+        """alpha*(K x)_local + shift*x_local from the symmetric tile storage; ``partial=True`` returns this
+        rank's full-length partial product (no collective) instead."""
+        assert x_full.is_contiguous() and x_full.numel() >= self.n
+        nb = ctypes.c_int64()
+        _lib.check(self.lib.mlffpc_symop_workspace_bytes(self.ctx, ctypes.byref(nb)))
+        ws = self._ws('symop', nb.value)
+        if partial:
+            world = self._layout_world()
+            ppr = (self.M + world - 1) // world
+            pout = torch.zeros(world * ppr * self.dim_i, dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.mlffpc_symop_apply(self.ctx, _ptr(Ksym), _ptr(x_full), ctypes.c_void_p(0), 1.0, 0.0,
+                                                   _ptr(ws), nb.value, _ptr(pout), self._stream()))
+            return pout[:self.n]
+        if out is None:
+            out = self.empty(self.n_local)
+        _lib.check(self.lib.mlffpc_symop_apply(self.ctx, _ptr(Ksym), _ptr(x_full), _ptr(out), float(alpha),
+                                               float(shift), _ptr(ws), nb.value, ctypes.c_void_p(0), self._stream()))
+        return out
+
+    def _layout_world(self):
+        return getattr(self, '_lay_world', self.world)
+
     def matvec_free(self, v, alpha=1.0, shift=0.0, out=None):
         """alpha*(K v)_local + shift*v_local for the full n-vector v (predict.py:400-449,997-1052)."""
         assert v.numel() >= self.n and v.is_contiguous()

@@ -132,8 +132,6 @@ class Iterative(object):
         mode = task.get('kernel_mode', 'auto')
         if mode not in ('auto', 'assembled', 'assembled_sym', 'matrix_free'):
             raise ValueError("task['kernel_mode'] must be 'auto', 'assembled', 'assembled_sym' or 'matrix_free'")
-        if mode == 'assembled_sym' and self.engine.world > 1:
-            mode = 'assembled'  # the symmetric matvec is single-GPU; row-block shards use the plain GEMV
         if mode != 'auto':
             return mode
         eng = self.engine
@@ -206,8 +204,10 @@ class Iterative(object):
         t0 = timeit.default_timer()
         self.K_local = None
         eng.set_option('symmetric_gemv', 1 if mode == 'assembled_sym' else 0)
-        if mode in ('assembled', 'assembled_sym'):
+        if mode == 'assembled':
             self.K_local = eng.kernel_assemble(out=task.get('_K_buffer'))
+        elif mode == 'assembled_sym':  # symmetric tile storage: half the bytes per matvec and per rank
+            self.K_local = eng.symop_assemble(out=task.get('_K_buffer'))
         sync()
         self.timings['assemble'] = timeit.default_timer() - t0
         self.timings['kernel_mode'] = mode

@@ -36,6 +36,8 @@ class KernelOperator(_DeviceOperator):
 
     def device_apply(self, v):
         e = self.engine
+        if self.K_local is not None and self.K_local.dim() == 1:  # symmetric tile storage
+            return e.symop_apply(self.K_local, v, alpha=self.sign, shift=-self.sign * self.lam)
         if self.K_local is not None:
             return e.gemv(self.K_local, v, alpha=self.sign, shift=-self.sign * self.lam, x_off=e.row0)
         return e.matvec_free(v, alpha=self.sign, shift=-self.sign * self.lam)

@@ -1,37 +1,49 @@
 #!/bin/bash
-# Round-1 ncu evidence (run under gpurun, one GPU).  Numbers printed by runs under ncu are never bench values.
-# Every ncu run is bounded (-c) and wrapped in `timeout`: an unbounded launch list of a 38 700-launch step
-# costs ~80 ms per launch under ncu and never finishes.
+# Round-1 GPU evidence (run under gpurun, one GPU).  Numbers printed by runs under ncu are never bench values.
+# ncu sees only the library's profiler windows (MLFFPC_PROFILE -> cudaProfilerStart/Stop around chosen
+# pivot steps / CG iterations / factor phases; --profile-from-start off), so a 38 000-launch solve yields a
+# ~40-launch list instead of an hour of serialised replays.
 set -u
 mkdir -p gpurun_out
-HEAD="python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline"            # the headline command (cfg2, tol 1e-6)
-PROF="python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --tol 1e-3"   # same kernels, shorter CG
-SYM="$PROF --mode assembled_sym"
-NCU="ncu --clock-control none"
+T0=$(date +%s)
+stamp() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
+B="python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline"
+NCU="ncu --clock-control none --profile-from-start off"
+WIN="assemble:0:1,pchol:3000:2,syrk:0:1,potrf:10:1,trsm:20:1,pcg:5:2"
 
-# (1) launch lists: two 300-launch windows of the headline step (pivoted-Cholesky phase, PCG phase)
-$HEAD > gpurun_out/r01_head_plain.log 2>&1 && {
-  timeout 400 $NCU --metrics gpu__time_duration.sum -s 12000 -c 300 --csv \
-      --log-file gpurun_out/r01_launches_pchol_window.csv $HEAD > /dev/null 2>&1; echo "list pchol rc=$?"
-  timeout 400 $NCU --metrics gpu__time_duration.sum -s 26000 -c 320 --csv \
-      --log-file gpurun_out/r01_launches_pcg_window.csv $HEAD > /dev/null 2>&1; echo "list pcg rc=$?"
+# (0) parity first
+python -m pytest tests -m gpu -x -q > gpurun_out/r01_gpu_tests.log 2>&1; stamp "gpu tests rc=$?"
+tail -3 gpurun_out/r01_gpu_tests.log
+
+# (1) fp64 GEMM rates (cuBLAS vs our DMMA kernel)
+python scripts/fp64_peak.py > gpurun_out/r01_fp64_peak.json 2> gpurun_out/r01_fp64_peak.err; stamp "fp64 peak rc=$?"
+
+# (2) operator comparison at the headline size, short CG (tol 1e-3): plain GEMV, symmetric, matrix-free
+for mode in assembled assembled_sym matrix_free; do
+  $B --tol 1e-3 --mode $mode > gpurun_out/r01_mode_$mode.json 2> gpurun_out/r01_mode_$mode.err; stamp "mode $mode rc=$?"
+done
+
+# (3) launch list: the headline command (tol 1e-6), profiler windows only
+$B > gpurun_out/r01_head_plain.log 2>&1 && {
+  stamp "head plain ok"
+  MLFFPC_PROFILE=$WIN timeout 900 $NCU --metrics gpu__time_duration.sum --csv \
+      --log-file gpurun_out/r01_launches_windows.csv $B > gpurun_out/r01_launches_stdout.log 2>&1
+  stamp "launch list rc=$?"
 }
 
-# (2) full captures of the hot kernels at the headline size (n = 108 000)
-$PROF > gpurun_out/r01_prof_plain.log 2>&1 && {
-  timeout 300 $NCU --set full --import-source on -k regex:gemv_rows_kernel -s 2 -c 2 \
-      -o gpurun_out/r01_gemv -f $PROF > /dev/null 2>&1; echo "gemv rc=$?"
-  timeout 300 $NCU --set full --import-source on -k regex:pchol_update_kernel -s 3000 -c 2 \
-      -o gpurun_out/r01_pchol_update -f $PROF > /dev/null 2>&1; echo "pchol rc=$?"
-  timeout 300 $NCU --set full --import-source on -k regex:tgemv_cols_kernel -s 2 -c 1 \
-      -o gpurun_out/r01_tgemv -f $PROF > /dev/null 2>&1; echo "tgemv rc=$?"
-  timeout 300 $NCU --set full --import-source on -k regex:dgemm_kernel -s 1 -c 1 \
-      -o gpurun_out/r01_dgemm -f $PROF > /dev/null 2>&1; echo "dgemm rc=$?"
-  timeout 300 $NCU --set full --import-source on -k regex:assemble_block_kernel -s 1 -c 1 \
-      -o gpurun_out/r01_assemble -f $PROF > /dev/null 2>&1; echo "assemble rc=$?"
+# (4) full captures of the hot kernels inside the same windows (short CG so the run is brief)
+P="$B --tol 1e-2"
+$P > gpurun_out/r01_prof_plain.log 2>&1 && {
+  stamp "prof plain ok"
+  MLFFPC_PROFILE=$WIN timeout 900 $NCU --set full --import-source on \
+      -k regex:'gemv_rows_kernel|tgemv_cols_kernel|pchol_update_kernel|assemble_block_kernel|dgemm_kernel' -c 14 \
+      -o gpurun_out/r01_hot -f $P > gpurun_out/r01_hot_stdout.log 2>&1
+  stamp "hot capture rc=$?"
 }
-$SYM > gpurun_out/r01_sym_plain.log 2>&1 && {
-  timeout 300 $NCU --set full --import-source on -k regex:symv_strip_kernel -s 2 -c 1 \
-      -o gpurun_out/r01_symv -f $SYM > /dev/null 2>&1; echo "symv rc=$?"
+S="$B --tol 1e-2 --mode assembled_sym"
+$S > gpurun_out/r01_sym_plain.log 2>&1 && {
+  MLFFPC_PROFILE=pcg:5:1 timeout 600 $NCU --set full --import-source on -k regex:'symv_' -c 2 \
+      -o gpurun_out/r01_symv -f $S > gpurun_out/r01_symv_stdout.log 2>&1
+  stamp "symv capture rc=$?"
 }
 ls -la gpurun_out/

@@ -68,7 +68,8 @@ def main():
     assert float((mv - ref.matvec_free(v)[sl]).norm() / mv.norm()) < 1e-12
 
     # full solves through the public entry point, sharded vs single GPU
-    for mode, variant in (('assembled', 'cholesky'), ('matrix_free', 'cholesky'), ('assembled', 'random_scores')):
+    for mode, variant in (('assembled', 'cholesky'), ('assembled_sym', 'cholesky'), ('matrix_free', 'cholesky'),
+                          ('assembled', 'random_scores')):
         out = {}
         for tag, distributed in (('sharded', True), ('single', False)):
             task = dict(inp['task'])
@@ -88,6 +89,13 @@ def main():
         assert np.array_equal(out['sharded'][2], out['single'][2])
         if rank == 0:
             print('  %s/%s: iters sharded %d single %d, |dalpha|/|alpha| = %.2e' % (mode, variant, i1, i0, d), flush=True)
+
+    # symmetric tile operator with the real reduce-scatter
+    Ksym = eng.symop_assemble()
+    sv = eng.symop_apply(Ksym, v, alpha=-1.0, shift=lam)
+    gv = ref.gemv(K_ref, v, alpha=-1.0, shift=lam)[sl]
+    assert float((sv - gv).norm() / gv.norm()) < 1e-12
+    del Ksym
 
     # replicated-vector helper
     full = allgather_rows(eng, a[sl].contiguous())

@@ -188,3 +188,49 @@ def test_world2_gloo():
         p.join(timeout=60)
     for rank, msg in res:
         assert msg == 'ok', 'rank %d: %s' % (rank, msg)
+
+
+def test_symop_plan_covers_every_block_pair_once_and_balances():
+    """The symmetric tile plan (csrc/symop.cu, host mirror dist.symop_plan): every matrix entry of the
+    lower-or-upper triangle is owned by exactly one rank, and the ranks read (nearly) equal shares."""
+    from mlff_preconditioner_b200.dist import symop_entries_read, symop_plan
+
+    for M, world in [(12, 1), (12, 2), (13, 2), (12, 3), (12, 4), (15, 4), (40, 8), (43, 8), (4000, 8), (10, 5), (13, 5)]:
+        cover = np.zeros((M, M), dtype=np.int32)     # per point pair (i, j): how many ranks touch it (either side)
+        reads = []
+        for r in range(world):
+            tiles = symop_plan(M, world, r)
+            assert tiles[0][4] == 1 and tiles[0][0] == tiles[0][2]      # the diagonal tile comes first
+            for (i0, i1, j0, j1, diag) in tiles:
+                if diag:
+                    blk = np.tril(np.ones((i1 - i0, i1 - i0), dtype=np.int32))
+                    cover[i0:i1, j0:j1] += blk
+                    cover[j0:j1, i0:i1] += np.tril(blk, -1).T
+                else:
+                    cover[i0:i1, j0:j1] += 1
+                    cover[j0:j1, i0:i1] += 1
+            reads.append(symop_entries_read(tiles, 27))
+        assert (cover == 1).all(), (M, world)
+        if M % world == 0 and M >= 8 * world:
+            assert max(reads) <= 1.15 * min(reads), (M, world, reads)
+            assert sum(reads) <= 0.56 * (27 * M) ** 2                 # about half of the full matrix
+
+
+def test_symop_numpy_emulation_matches_full_matvec():
+    """Sum over ranks of (tile rows A x_cols  +  tile columns A^T x_rows) == K x, on a golden kernel matrix."""
+    from mlff_preconditioner_b200.dist import symop_plan
+
+    g = load_golden('eth_s1_m12')
+    K, M, di = g['K'], 12, 27
+    x = np.random.default_rng(0).standard_normal(K.shape[0])
+    for world in (1, 2, 3, 4, 5):
+        y = np.zeros_like(x)
+        for r in range(world):
+            for (i0, i1, j0, j1, diag) in symop_plan(M, world, r):
+                A = K[i0 * di:i1 * di, j0 * di:j1 * di]
+                if diag:
+                    y[i0 * di:i1 * di] += np.tril(A) @ x[j0 * di:j1 * di] + np.tril(A, -1).T @ x[i0 * di:i1 * di]
+                else:
+                    y[i0 * di:i1 * di] += A @ x[j0 * di:j1 * di]
+                    y[j0 * di:j1 * di] += A.T @ x[i0 * di:i1 * di]
+        assert np.linalg.norm(y - K @ x) <= 1e-13 * np.linalg.norm(K @ x), world

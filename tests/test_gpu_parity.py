@@ -301,3 +301,46 @@ def test_against_oracle_seeded(torch_cuda, kind, M, perm_kind):
     T = eng.woodbury_factor_(Lt, lam)
     out = eng.precon_apply(T, lam, 1.0, torch.as_tensor(a, device=eng.device)).cpu().numpy()
     assert relerr(out, orc.woodbury_apply(T_ref, lam, a)) < TOL
+
+
+@pytest.mark.parametrize('case', OP_CASES)
+def test_symmetric_tile_operator_emulated_ranks(torch_cuda, golden, case):
+    """csrc/symop.cu: each emulated rank assembles only its tiles (half of its row block) and produces a
+    full-length partial product; the sum over ranks is K v (what the reduce-scatter computes on a real
+    multi-GPU run), for every world size including odd ones and ones that do not divide M."""
+    torch = torch_cuda
+    from mlff_preconditioner_b200.dist import symop_plan
+
+    g = golden(case)
+    eng = _engine(g)
+    lam = float(g['lam'])
+    v = torch.as_tensor(g['v'], device=eng.device)
+    Kv = g['K_op_v'] + lam * g['v']
+    M = eng.M
+    for world in [w for w in (1, 2, 3, 4, 5, 6) if (w - 1) * (-(-M // w)) < M]:
+        total = torch.zeros(eng.n, dtype=torch.float64, device=eng.device)
+        elems = 0
+        for rank in range(world):
+            eng.set_layout(rank, world)
+            tiles = eng.symop_tiles()
+            assert [t[:4] + (t[6],) for t in tiles] == symop_plan(M, world, rank)
+            Ksym = torch.full((eng.symop_storage_elems(),), float('nan'), dtype=torch.float64, device=eng.device)
+            eng.symop_assemble(out=Ksym)
+            elems += Ksym.numel()
+            # entries of the stored tiles equal the reference's K (diagonal tile: the part the strips read)
+            for (i0, i1, j0, j1, ld, off, diag) in tiles:
+                nr, nc = (i1 - i0) * eng.dim_i, (j1 - j0) * eng.dim_i
+                tile = Ksym[off:off + nr * ld].view(nr, ld)[:, :nc].cpu().numpy()
+                ref = g['K'][i0 * eng.dim_i:i1 * eng.dim_i, j0 * eng.dim_i:j1 * eng.dim_i]
+                if diag:
+                    tile, ref = np.tril(tile), np.tril(ref)
+                assert np.abs(tile - ref).max() <= TOL * np.abs(g['K']).max()
+            total += eng.symop_apply(Ksym, v, partial=True)
+        assert relerr(total.cpu().numpy(), Kv) < TOL, world
+        if world >= 4 and M % world == 0:
+            assert elems < 0.8 * eng.n * eng.n          # about half of the matrix is stored in total
+    eng.set_layout(0, 1)
+    Ksym = eng.symop_assemble()
+    out = eng.symop_apply(Ksym, v, alpha=1.0, shift=-lam).cpu().numpy()
+    assert relerr(out, g['K_op_v']) < TOL
+    assert np.array_equal(out, eng.symop_apply(Ksym, v, alpha=1.0, shift=-lam).cpu().numpy())  # deterministic
