@@ -238,6 +238,8 @@ def run_ours(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'  # the version banner goes to stdout; rank 0 prints exactly one JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     import __graft_entry__ as g
 
@@ -256,6 +258,7 @@ def run_ours(args):
     frac = (k + 0.5) / n  # int(frac * n) == k
     task = dict(inp['task'])
     task['kernel_mode'] = args.mode
+    task['_want_hist'] = True
     dev = torch.device('cuda', local_rank)
 
     def barrier():
@@ -349,7 +352,8 @@ def run_ours(args):
     phases = {'preconditioner_s': tm['preconditioner'], 'pchol_build_s': tm.get('pchol_build'),
               'assemble_s': tm['assemble'], 'cg_s': tm['cg'], 'cg_iters': iters, 'resid': resid,
               'rel_resid': resid / np.linalg.norm(inp['y']), 'converged': info == 0,
-              'precon_apply_avg_ms': pre_ms / max(op_calls, 1)}
+              'precon_apply_avg_ms': pre_ms / max(op_calls, 1),
+              'rel_resid_every_100_iters': [float('%.3g' % v) for v in tm['resid_hist_rel'][::100]]}
 
     # ---- end-to-end arm: host numpy in, host numpy out, through Iterative.solve -----------------------
     del it, out
@@ -418,7 +422,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--M', type=int, default=None, help='override the number of training points')
-    ap.add_argument('--mode', default='assembled', choices=['assembled', 'assembled_sym', 'matrix_free'])
+    ap.add_argument('--mode', default='assembled_sym', choices=['assembled', 'assembled_sym', 'matrix_free'],
+                    help='assembled_sym (default): symmetric tile storage, every entry read once per matvec; '
+                         'assembled: full row block + plain GEMV; matrix_free: on-the-fly operator')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer arm (profiling runs)')

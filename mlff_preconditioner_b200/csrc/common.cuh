@@ -138,18 +138,24 @@ int launch_gemv_rows(const double* K, int64_t n_rows, int64_t n_cols, int64_t ld
 int launch_tgemv_cols(const double* T, int64_t k, int64_t n_cols, int64_t ld, const double* w,
                       double* out, int post, const double* r, double sign_over_lam, int num_sms,
                       cudaStream_t s);
-// symmetric operator (symop.cu)
+// symmetric operator (symop.cu, symtma.cu)
 int64_t symv_ws_bytes(int64_t n);
-int launch_symv(const double* K, int64_t n, int64_t ld, const double* x, double* y, double alpha, double shift,
-                void* workspace, cudaStream_t s);
+int launch_symv(mlffpc_ctx* ctx, const double* K, int64_t n, int64_t ld, const double* x, double* y, double alpha,
+                double shift, void* workspace, cudaStream_t s);
 int64_t symop_storage_elems(const mlffpc_ctx* ctx);
 int64_t symop_ws_bytes(const mlffpc_ctx* ctx);
 int symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full, double* y_local, double alpha,
                 double shift, void* workspace, double* partial_out, cudaStream_t s);
-// explicit rectangle K[points i_pt0:i_pt1, points j_pt0:j_pt1] -> out (row-major, ld); diag_tr >= 0 skips the
-// point blocks right of the diagonal that a lower-triangle reader with diag_tr-row strips never touches
+int64_t symv_tma_ws_doubles(int64_t nr, int64_t nc);
+bool symv_tma_usable(const double* K, int64_t ld, int64_t nr);
+int symv_tile_tma(mlffpc_ctx* ctx, const double* K, int64_t ld, int64_t nr, int64_t nc, int diag, int packed,
+                  const double* xr, const double* xc, double* wsd, double* out_c, double* out_r,
+                  const double* x_shift, double alpha, double shift, cudaStream_t s);
+// explicit rectangle K[points i_pt0:i_pt1, points j_pt0:j_pt1] -> out; packed = 0: row-major with leading
+// dimension ld; packed = 1 (square diagonal tiles): the band layout of symlayout.cuh, entries right of a
+// band's pitch are not stored
 int assemble_tile(mlffpc_ctx* ctx, int64_t i_pt0, int64_t i_pt1, int64_t j_pt0, int64_t j_pt1, double* out,
-                  int64_t ld, int diag_tr, cudaStream_t s);
+                  int64_t ld, int packed, cudaStream_t s);
 // one column of scale*K on the local rows, column index read from device memory (geometry.cu)
 int launch_columns_device_col(mlffpc_ctx* ctx, const int64_t* col_dev, double* out, double scale,
                               cudaStream_t s);

@@ -74,6 +74,8 @@ struct NcclApi {
     nccl_errstr_fn errstr = nullptr;
 };
 static NcclApi g_nccl;
+static void* g_cached_comm = nullptr;  // process-lifetime communicator (see mlffpc_comm_init)
+static int g_cached_rank = -1, g_cached_world = -1, g_cached_device = -1;
 
 static int nccl_load(const char* path) {
     if (g_nccl.lib) return MLFFPC_OK;
@@ -168,7 +170,7 @@ int mlffpc_create(mlffpc_ctx** out, int device) {
 
 int mlffpc_destroy(mlffpc_ctx* ctx) {
     if (!ctx) return MLFFPC_OK;
-    if (ctx->comm.comm && g_nccl.destroy) g_nccl.destroy(ctx->comm.comm);
+    if (ctx->comm.comm && ctx->comm.comm != g_cached_comm && g_nccl.destroy) g_nccl.destroy(ctx->comm.comm);
     if (ctx->scal) cudaFree(ctx->scal);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->partials) cudaFree(ctx->partials);
@@ -192,9 +194,20 @@ int mlffpc_comm_init(mlffpc_ctx* ctx, const char* libnccl_path, const void* id12
     if (world == 1) return MLFFPC_OK;
     MLFFPC_TRY(nccl_load(libnccl_path));
     MLFFPC_CUDA(cudaSetDevice(ctx->device));
+    // One communicator per process and (rank, world, device): creating one costs seconds, and a driver that
+    // builds an engine per solve (Iterative.solve) would pay it every time.  Every rank takes the same branch.
+    if (g_cached_comm && g_cached_rank == rank && g_cached_world == world && g_cached_device == ctx->device) {
+        ctx->comm.comm = g_cached_comm;
+        return MLFFPC_OK;
+    }
     NcclId id;
     memcpy(id.internal, id128, 128);
-    return nccl_check(g_nccl.comm_init_rank(&ctx->comm.comm, world, id, rank), "ncclCommInitRank");
+    MLFFPC_TRY(nccl_check(g_nccl.comm_init_rank(&ctx->comm.comm, world, id, rank), "ncclCommInitRank"));
+    if (!g_cached_comm) {
+        g_cached_comm = ctx->comm.comm;
+        g_cached_rank = rank; g_cached_world = world; g_cached_device = ctx->device;
+    }
+    return MLFFPC_OK;
 }
 
 int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value) {

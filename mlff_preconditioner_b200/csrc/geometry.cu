@@ -6,6 +6,7 @@
 //   K_ij = sum_p [ a_p u_ip u_jp^T - b_p J_i^T J_j^(p) ],  u_ip = J_i^T Delta_p,  u_jp = J_j^(p)T Delta_p
 // with the sparse Jacobian J[d, b_d] = +g_d, J[d, a_d] = -g_d (utils/desc.py:444-462) never inflated.
 #include "common.cuh"
+#include "symlayout.cuh"
 
 namespace mlffpc {
 
@@ -157,7 +158,7 @@ __device__ __forceinline__ double jtj_entry(const GeoView& g, const double* gi, 
 // ---- explicit block (i, j): one CTA -----------------------------------------------------
 // dynamic smem: ab[2S] | red[33] | u_i[S*dim_i] | u_j[S*dim_i]
 template <bool DIAG_ONLY>
-__global__ void assemble_block_kernel(GeoView g, int64_t pt0, int64_t j_pt0, int diag_tr,
+__global__ void assemble_block_kernel(GeoView g, int64_t pt0, int64_t j_pt0, int packed,
                                       double* __restrict__ out, int64_t ld) {
     extern __shared__ double sm[];
     double* sm_ab = sm;
@@ -169,7 +170,8 @@ __global__ void assemble_block_kernel(GeoView g, int64_t pt0, int64_t j_pt0, int
     const int64_t i = pt0 + il;
     const int64_t jl = DIAG_ONLY ? il : (int64_t)blockIdx.y;
     const int64_t j = DIAG_ONLY ? i : j_pt0 + jl;
-    if (!DIAG_ONLY && diag_tr >= 0 && (j - i - 1) * g.dim_i >= diag_tr) return;  // never read by the strip reader
+    // packed diagonal tile: band b of 256 rows keeps columns [0, 256 (b + 1)); skip point blocks right of that
+    if (!DIAG_ONLY && packed && jl * g.dim_i >= st_band_pitch(((il + 1) * g.dim_i - 1) / ST_BAND_ROWS)) return;
     const double* xi = g.R_desc + i * g.D;
     const double* gi = g.R_d_desc + i * g.D * 3;
     const double* gj = g.R_d_desc + j * g.D * 3;
@@ -199,12 +201,18 @@ __global__ void assemble_block_kernel(GeoView g, int64_t pt0, int64_t j_pt0, int
         double* blk = out + (il * g.dim_i) * ld + jl * g.dim_i;
         for (int t = threadIdx.x; t < nent; t += blockDim.x) {
             const int r = t / g.dim_i, r2 = t % g.dim_i;
+            double* dst = blk + (int64_t)r * ld + r2;
+            if (packed) {
+                const int64_t row = il * g.dim_i + r, col = jl * g.dim_i + r2, b = row / ST_BAND_ROWS;
+                if (col >= st_band_pitch(b)) continue;
+                dst = out + st_band_off(b) + (row - b * ST_BAND_ROWS) * st_band_pitch(b) + col;
+            }
             double val = 0.0;
             for (int p = 0; p < g.S; ++p) {
                 const double G = jtj_entry(g, gi, gj, g.P + p * g.N, g.Pinv + p * g.N, r / 3, r % 3, r2 / 3, r2 % 3);
                 val += sm_ab[2 * p] * sm_ui[p * g.dim_i + r] * sm_uj[p * g.dim_i + r2] - sm_ab[2 * p + 1] * G;
             }
-            blk[(int64_t)r * ld + r2] = val;
+            *dst = val;
         }
     }
 }
@@ -332,7 +340,7 @@ int mlffpc_kernel_diag(mlffpc_ctx* ctx, double* out, void* stream) {
     MLFFPC_CUDA(cudaFuncSetAttribute(assemble_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int block = pick_block(g.D < g.dim_i ? g.dim_i : g.D);
     assemble_block_kernel<true><<<dim3((unsigned)(ctx->pt1 - ctx->pt0)), block, smem, (cudaStream_t)stream>>>(
-        g, ctx->pt0, 0, -1, out, 0);
+        g, ctx->pt0, 0, 0, out, 0);
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;
 }
@@ -342,7 +350,7 @@ int mlffpc_kernel_assemble(mlffpc_ctx* ctx, double* K_out, int64_t ld, void* str
     MLFFPC_REQUIRE(ld >= ctx->n, "kernel_assemble: ld %lld < n %lld", (long long)ld, (long long)ctx->n);
     ProfWindow pw = prof_window("assemble");
     pw.step(pw.first);
-    const int st = assemble_tile(ctx, ctx->pt0, ctx->pt1, 0, ctx->M, K_out, ld, -1, (cudaStream_t)stream);
+    const int st = assemble_tile(ctx, ctx->pt0, ctx->pt1, 0, ctx->M, K_out, ld, 0, (cudaStream_t)stream);
     pw.end();
     return st;
 }
@@ -379,10 +387,12 @@ int mlffpc_kernel_columns(mlffpc_ctx* ctx, const int64_t* cols, int64_t b, doubl
 
 namespace mlffpc {
 int assemble_tile(mlffpc_ctx* ctx, int64_t i_pt0, int64_t i_pt1, int64_t j_pt0, int64_t j_pt1, double* out,
-                  int64_t ld, int diag_tr, cudaStream_t s) {
+                  int64_t ld, int packed, cudaStream_t s) {
     MLFFPC_REQUIRE(0 <= i_pt0 && i_pt0 < i_pt1 && i_pt1 <= ctx->M && 0 <= j_pt0 && j_pt0 < j_pt1 && j_pt1 <= ctx->M,
                    "assemble_tile: bad point ranges");
-    MLFFPC_REQUIRE(ld >= (j_pt1 - j_pt0) * ctx->dim_i, "assemble_tile: ld too small");
+    MLFFPC_REQUIRE(packed ? (i_pt0 == j_pt0 && i_pt1 == j_pt1) : (ld >= (j_pt1 - j_pt0) * ctx->dim_i),
+                   "assemble_tile: ld too small / packed layout needs a square diagonal tile");
+    MLFFPC_REQUIRE(!packed || (j_pt1 - j_pt0) <= 65535, "assemble_tile: packed tiles are limited to 65535 points");
     GeoView g = make_view(ctx);
     const size_t smem = (size_t)(2 * g.S + 40 + 2 * g.S * g.dim_i) * sizeof(double);
     MLFFPC_REQUIRE(smem <= 200 * 1024, "kernel_assemble: S*3N = %d too large for shared memory", g.S * g.dim_i);
@@ -391,7 +401,7 @@ int assemble_tile(mlffpc_ctx* ctx, int64_t i_pt0, int64_t i_pt1, int64_t j_pt0, 
     for (int64_t j0 = j_pt0; j0 < j_pt1; j0 += 65535) {  // grid.y limit
         const int64_t nj = (j_pt1 - j0 < 65535) ? (j_pt1 - j0) : 65535;
         assemble_block_kernel<false><<<dim3((unsigned)(i_pt1 - i_pt0), (unsigned)nj), block, smem, s>>>(
-            g, i_pt0, j0, diag_tr, out + (j0 - j_pt0) * g.dim_i, ld);
+            g, i_pt0, j0, packed, packed ? out : out + (j0 - j_pt0) * g.dim_i, ld);
         MLFFPC_LAUNCH_CHECK();
     }
     return MLFFPC_OK;

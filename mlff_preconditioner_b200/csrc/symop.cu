@@ -13,9 +13,14 @@
 // strip partials.  Across ranks the full-length partial results are combined with one reduce-scatter
 // (n doubles) -- the only extra collective next to the allgather of the search direction.
 // HBM traffic per matvec and rank: 4 n n_local (1 + 2/32) bytes instead of 8 n n_local.
+// The diagonal tile is stored packed (bands of 256 rows holding only the columns left of and including
+// their diagonal blocks, symlayout.cuh), so the storage is half of the row block as well.  The tile passes
+// run on the persistent TMA kernel of symtma.cu; symv_tile_kernel below is the register-staged fallback
+// for a caller-owned square K whose base or pitch is not 16-byte aligned (mlffpc_symv).
 #include <vector>
 
 #include "common.cuh"
+#include "symlayout.cuh"
 
 namespace mlffpc {
 
@@ -166,8 +171,8 @@ __global__ void symop_finish_kernel(const double* __restrict__ q, const double* 
 // ---- tile plan -------------------------------------------------------------------------------------
 struct SymTile {
     int64_t i_pt0, i_pt1, j_pt0, j_pt1;  // point ranges (rows, columns)
-    int64_t nr, nc, ld, off;             // rows, columns, leading dimension, element offset in the storage
-    int diag;
+    int64_t nr, nc, ld, off;             // rows, columns, leading dimension (0: packed), element offset
+    int diag;                            // diagonal tiles use the packed band layout of symlayout.cuh
 };
 
 static inline int64_t up32(int64_t x) { return (x + 31) / 32 * 32; }
@@ -185,9 +190,9 @@ static std::vector<SymTile> symop_plan(const mlffpc_ctx* c, int64_t* total_elems
         SymTile t;
         t.i_pt0 = i0; t.i_pt1 = i1; t.j_pt0 = j0; t.j_pt1 = j1;
         t.nr = (i1 - i0) * di; t.nc = (j1 - j0) * di;
-        t.ld = (t.nc + 1) & ~(int64_t)1;
+        t.ld = diag ? 0 : ((t.nc + 1) & ~(int64_t)1);
         t.off = off; t.diag = diag;
-        off = up32(off + t.nr * t.ld);
+        off = up32(off + (diag ? st_packed_elems(t.nr) : t.nr * t.ld));
         tiles.push_back(t);
     };
     add(blk0(g), blk1(g), blk0(g), blk1(g), 1);
@@ -210,27 +215,22 @@ static std::vector<SymTile> symop_plan(const mlffpc_ctx* c, int64_t* total_elems
 }
 
 struct SymWs {
-    int64_t n_pad, ld_ws, off_y1, off_ws, off_yp, off_q, total;
+    int64_t n_pad, off_tile, off_yp, off_q, total;
 };
 static SymWs symop_ws_layout(const mlffpc_ctx* c, const std::vector<SymTile>& tiles) {
     auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
     SymWs w;
     const int W = c->lay_world;
     w.n_pad = ((c->M + W - 1) / W) * c->dim_i;
-    int64_t max_nr = 0, max_nc = 0, max_ws = 0;
+    int64_t max_ws = 0;
     for (const auto& t : tiles) {
-        if (t.nr > max_nr) max_nr = t.nr;
-        if (t.nc > max_nc) max_nc = t.nc;
-        const int64_t ns = (t.nr + SYMV_TR - 1) / SYMV_TR;
-        const int64_t e = ns * ((t.nc + 1) & ~(int64_t)1);
+        const int64_t e = symv_tma_ws_doubles(t.nr, t.nc);
         if (e > max_ws) max_ws = e;
     }
-    w.ld_ws = (max_nc + 1) & ~(int64_t)1;
     int64_t o = 0;
-    w.off_y1 = o; o = up(o + (max_nr + 64) * 8);
-    w.off_ws = o; o = up(o + (max_ws + 64) * 8);
-    w.off_yp = o; o = up(o + (W > 1 ? (int64_t)W * w.n_pad * 8 : 0));
-    w.off_q = o;  o = up(o + (W > 1 ? w.n_pad * 8 : 0));
+    w.off_tile = o; o = up(o + max_ws * 8);
+    w.off_yp = o; o = up(o + (int64_t)W * w.n_pad * 8);
+    w.off_q = o;  o = up(o + w.n_pad * 8);
     w.total = o + 512;
     return w;
 }
@@ -244,17 +244,15 @@ int64_t symop_ws_bytes(const mlffpc_ctx* ctx) {
     return symop_ws_layout(ctx, symop_plan(ctx, nullptr)).total;
 }
 
-// one tile: strip pass + partial reduction.  out_c/out_r/x_shift as in symv_reduce_kernel.
-static int symv_tile(const double* K, int64_t ld, int64_t nr, int64_t nc, int diag, const double* xr,
-                     const double* xc, double* y1, double* ws, double* out_c, double* out_r,
-                     const double* x_shift, double alpha, double shift, cudaStream_t s) {
-    const int64_t nstrips = (nr + SYMV_TR - 1) / SYMV_TR;
-    const int64_t ld_ws = (nc + 1) & ~(int64_t)1;
-    symv_tile_kernel<SYMV_TR><<<(unsigned)nstrips, SYMV_THREADS, 0, s>>>(K, ld, nr, nc, diag, xr, xc, y1, ws, ld_ws);
+// register-staged fallback: strip pass + partial reduction on a square row-major K
+static int symv_square_fallback(const double* K, int64_t ld, int64_t n, const double* x, double* y1, double* ws,
+                                double* y, double alpha, double shift, cudaStream_t s) {
+    const int64_t nstrips = (n + SYMV_TR - 1) / SYMV_TR;
+    const int64_t ld_ws = (n + 1) & ~(int64_t)1;
+    symv_tile_kernel<SYMV_TR><<<(unsigned)nstrips, SYMV_THREADS, 0, s>>>(K, ld, n, n, 1, x, x, y1, ws, ld_ws);
     MLFFPC_LAUNCH_CHECK();
-    const int64_t work = diag ? nc : nc + nr;
-    symv_reduce_kernel<SYMV_TR><<<(unsigned)((work + 255) / 256), 256, 0, s>>>(y1, ws, ld_ws, nr, nc, nstrips, diag,
-                                                                             out_c, out_r, x_shift, alpha, shift);
+    symv_reduce_kernel<SYMV_TR><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y1, ws, ld_ws, n, n, nstrips, 1, y, nullptr,
+                                                                          x, alpha, shift);
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;
 }
@@ -262,18 +260,20 @@ static int symv_tile(const double* K, int64_t ld, int64_t nr, int64_t nc, int di
 int64_t symv_ws_bytes(int64_t n) {
     const int64_t nstrips = (n + SYMV_TR - 1) / SYMV_TR;
     const int64_t ld_ws = (n + 1) & ~(int64_t)1;
-    return (nstrips * ld_ws + n + 128) * 8 + 512;
+    const int64_t fallback = nstrips * ld_ws + n + 128;
+    const int64_t tma = symv_tma_ws_doubles(n, n);
+    return (fallback > tma ? fallback : tma) * 8 + 512;
 }
 
 // y = alpha * K x + shift * x for one symmetric square K (only the lower triangle by strips is read)
-int launch_symv(const double* K, int64_t n, int64_t ld, const double* x, double* y, double alpha, double shift,
-                void* workspace, cudaStream_t s) {
+int launch_symv(mlffpc_ctx* ctx, const double* K, int64_t n, int64_t ld, const double* x, double* y, double alpha,
+                double shift, void* workspace, cudaStream_t s) {
+    double* wsd = (double*)(((uintptr_t)workspace + 255) / 256 * 256);
+    if (symv_tma_usable(K, ld, n))
+        return symv_tile_tma(ctx, K, ld, n, n, 1, 0, x, x, wsd, y, nullptr, x, alpha, shift, s);
     MLFFPC_REQUIRE(ld % 2 == 0 && ((uintptr_t)K % 16 == 0),
                    "symv: K must be 16-byte aligned with an even leading dimension");
-    double* wsd = (double*)(((uintptr_t)workspace + 255) / 256 * 256);
-    double* y1 = wsd;
-    double* ws = wsd + ((n + 63) / 32 * 32);
-    return symv_tile(K, ld, n, n, 1, x, x, y1, ws, y, nullptr, x, alpha, shift, s);
+    return symv_square_fallback(K, ld, n, x, wsd, wsd + ((n + 63) / 32 * 32), y, alpha, shift, s);
 }
 
 // The sharded symmetric operator on this rank's tiles.  With partial_out != NULL the full-length partial
@@ -283,22 +283,21 @@ int symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full, doubl
     const std::vector<SymTile> tiles = symop_plan(ctx, nullptr);
     const SymWs w = symop_ws_layout(ctx, tiles);
     char* base = (char*)(((uintptr_t)workspace + 255) / 256 * 256);
-    double* y1 = (double*)(base + w.off_y1);
-    double* ws = (double*)(base + w.off_ws);
+    double* wt = (double*)(base + w.off_tile);
     const int W = ctx->lay_world;
     const int64_t di = ctx->dim_i;
     if (W == 1 && !partial_out) {
         const SymTile& t = tiles[0];
-        return symv_tile(Ksym + t.off, t.ld, t.nr, t.nc, 1, x_full, x_full, y1, ws, y_local, nullptr, x_full, alpha,
-                         shift, s);
+        return symv_tile_tma(ctx, Ksym + t.off, 0, t.nr, t.nc, 1, 1, x_full, x_full, wt, y_local, nullptr, x_full,
+                             alpha, shift, s);
     }
     double* yp = partial_out ? partial_out : (double*)(base + w.off_yp);
     MLFFPC_CUDA(cudaMemsetAsync(yp, 0, (size_t)W * w.n_pad * 8, s));
     for (const auto& t : tiles) {
         const double* xr = x_full + t.i_pt0 * di;
         const double* xc = x_full + t.j_pt0 * di;
-        MLFFPC_TRY(symv_tile(Ksym + t.off, t.ld, t.nr, t.nc, t.diag, xr, xc, y1, ws, yp + t.j_pt0 * di,
-                             yp + t.i_pt0 * di, nullptr, 1.0, 0.0, s));
+        MLFFPC_TRY(symv_tile_tma(ctx, Ksym + t.off, t.ld, t.nr, t.nc, t.diag, t.diag, xr, xc, wt, yp + t.j_pt0 * di,
+                                 yp + t.i_pt0 * di, nullptr, 1.0, 0.0, s));
     }
     if (partial_out) return MLFFPC_OK;
     MLFFPC_REQUIRE(ctx->comm.world == W, "symop_apply: the tile layout (%d ranks) needs a communicator of that size", W);
@@ -313,7 +312,7 @@ int symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full, doubl
 int symop_assemble(mlffpc_ctx* ctx, double* Ksym, cudaStream_t s) {
     const std::vector<SymTile> tiles = symop_plan(ctx, nullptr);
     for (const auto& t : tiles)
-        MLFFPC_TRY(assemble_tile(ctx, t.i_pt0, t.i_pt1, t.j_pt0, t.j_pt1, Ksym + t.off, t.ld, t.diag ? SYMV_TR : -1, s));
+        MLFFPC_TRY(assemble_tile(ctx, t.i_pt0, t.i_pt1, t.j_pt0, t.j_pt1, Ksym + t.off, t.ld, t.diag ? 1 : 0, s));
     return MLFFPC_OK;
 }
 
@@ -334,7 +333,7 @@ int mlffpc_symv(mlffpc_ctx* ctx, const double* K, int64_t n, int64_t ld, const d
     MLFFPC_REQUIRE(ctx && K && x && y && workspace, "symv: NULL argument");
     MLFFPC_REQUIRE(n > 0 && ld >= n, "symv: bad dimensions");
     MLFFPC_REQUIRE(workspace_bytes >= symv_ws_bytes(n), "symv: workspace too small");
-    return launch_symv(K, n, ld, x, y, alpha, shift, workspace, (cudaStream_t)stream);
+    return launch_symv(ctx, K, n, ld, x, y, alpha, shift, workspace, (cudaStream_t)stream);
 }
 
 int mlffpc_symop_storage_elems(mlffpc_ctx* ctx, int64_t* elems) {

@@ -197,6 +197,20 @@ class Engine(object):
         _lib.check(self.lib.mlffpc_symop_tiles(self.ctx, buf, nt.value, ctypes.byref(nt)))
         return [tuple(buf[8 * i + j] for j in range(7)) for i in range(nt.value)]
 
+    @staticmethod
+    def symop_unpack_diag(Ksym, off, nr):
+        """Dense [nr, nr] view (copy) of a packed diagonal tile: band b = rows [256 b, 256 b + 256) stores the
+        columns [0, 256 (b + 1)) with that pitch (csrc/symlayout.cuh); entries that are not stored come back NaN."""
+        out = torch.full((nr, nr), float('nan'), dtype=torch.float64, device=Ksym.device)
+        for b in range((nr + 255) // 256):
+            r0, r1 = 256 * b, min(nr, 256 * b + 256)
+            pitch = 256 * (b + 1)
+            o = off + 65536 * (b * (b + 1) // 2)
+            band = Ksym[o:o + (r1 - r0) * pitch].view(r1 - r0, pitch)
+            w = min(pitch, nr)
+            out[r0:r1, :w] = band[:, :w]
+        return out
+
     def symop_storage_elems(self):
         ne = ctypes.c_int64()
         _lib.check(self.lib.mlffpc_symop_storage_elems(self.ctx, ctypes.byref(ne)))

@@ -214,9 +214,12 @@ class Iterative(object):
 
         maxiter = 3 * n_atoms * n_train * 5  # :1002
         tic_start = timeit.default_timer()
-        x, iters, resid, info, bnrm2 = eng.pcg(
+        res = eng.pcg(
             y_t[eng.row0:eng.row0 + eng.n_local].contiguous(), lam, task['solver_tol'], maxiter,
-            K_local=self.K_local, T=P_op.T, precon_sign=P_op.sign, x0=x0)
+            K_local=self.K_local, T=P_op.T, precon_sign=P_op.sign, x0=x0, want_hist=bool(task.get('_want_hist')))
+        x, iters, resid, info, bnrm2 = res[:5]
+        if task.get('_want_hist'):
+            self.timings['resid_hist_rel'] = res[5] / bnrm2
         sync()
         total_time_cg = timeit.default_timer() - tic_start
         self.timings.update(cg=total_time_cg, preconditioner=total_time_preconditioner, cg_iters=iters, k=k_rank,
