@@ -30,11 +30,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (structure, M, tol)
-    'cfg2': ('ethanol', 4000, 1e-6),
+    # name: (structure, M, tol)   -- BASELINE.json configs[0..4]; cfg2 is the single-GPU headline
+    'cfg1': ('nanotube', 9, 1e-6),        # N = 370, n = 9 990 (the reference's own CPU-runnable case)
+    'cfg2': ('ethanol', 4000, 1e-6),      # N = 9, n = 108 000, assembled on one B200
+    'cfg4': ('ethanol', 10000, 1e-6),     # n = 270 000, sharded over >= 4 B200 (symmetric tile storage)
+    'cfg5': ('aspirin', 20000, 1e-6),     # N = 21, n = 1 260 000, matrix-free over 8 B200
     'cfg2_mid': ('ethanol', 1500, 1e-6),
     'small': ('ethanol', 300, 1e-6),
 }
+# rule-of-thumb parameters (m, k_min) per molecule (reference src/tools/plot_data.py:677-706)
+RULE_OF_THUMB = {'ethanol': (0.87, 10), 'aspirin': (1.14, 236), 'nanotube': (0.73, 89)}
 CONSTANTS_FILE = os.path.join(ROOT, 'bench_constants.json')
 
 
@@ -60,7 +65,8 @@ def make_inputs(workload, M_override=None, tol_override=None, k_override=None):
     y_std = np.std(y)
     y /= y_std
     n = 3 * N * M
-    k = min(rule_of_thumb(n, 10, 0.87), n // 4)  # ethanol parameters (plot_data.py:677-706)
+    m_rt, kmin_rt = RULE_OF_THUMB.get(kind, RULE_OF_THUMB['ethanol'])
+    k = min(rule_of_thumb(n, kmin_rt, m_rt), n // 4)
     if k_override:
         k = k_override
     if tol_override:

@@ -212,7 +212,7 @@ class Iterative(object):
         self.timings['assemble'] = timeit.default_timer() - t0
         self.timings['kernel_mode'] = mode
 
-        maxiter = 3 * n_atoms * n_train * 5  # :1002
+        maxiter = int(task.get('_maxiter', 3 * n_atoms * n_train * 5))  # :1002 (5 n; '_maxiter' caps sweeps)
         tic_start = timeit.default_timer()
         res = eng.pcg(
             y_t[eng.row0:eng.row0 + eng.n_local].contiguous(), lam, task['solver_tol'], maxiter,

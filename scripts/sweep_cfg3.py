@@ -22,7 +22,7 @@ def main():
     ap.add_argument('--kind', default='ethanol')
     ap.add_argument('--ks', default='100,200,500,1000,2000,5000')
     ap.add_argument('--variants', default='cholesky,random_scores,lev_random,truncated_cholesky')
-    ap.add_argument('--mode', default='assembled', choices=['assembled', 'matrix_free'])
+    ap.add_argument('--mode', default='assembled', choices=['assembled', 'assembled_sym', 'matrix_free'])
     ap.add_argument('--tol', type=float, default=1e-6)
     ap.add_argument('--maxiter', type=int, default=None)
     args = ap.parse_args()
@@ -39,8 +39,12 @@ def main():
     y_t = torch.as_tensor(inp['y'], device=eng.device)
     task = dict(inp['task'])
     task['kernel_mode'] = args.mode
+    if args.maxiter:
+        task['_maxiter'] = args.maxiter
     if args.mode == 'assembled':
         task['_K_buffer'] = eng.empty(eng.n_local, eng.n)
+    elif args.mode == 'assembled_sym':
+        task['_K_buffer'] = eng.empty(eng.symop_storage_elems())
     for variant in args.variants.split(','):
         for k in [int(x) for x in args.ks.split(',')]:
             frac = (k + 0.5) / n

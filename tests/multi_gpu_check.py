@@ -31,9 +31,13 @@ def main():
     from mlff_preconditioner_b200.engine import Engine
     from mlff_preconditioner_b200.solvers.iterative_solver import Iterative
 
-    WORKLOADS['mg'] = ('ethanol', 203, 1e-5)   # M not divisible by the world size on purpose
+    # default: M not divisible by the world size on purpose.  MG_M / MG_K run the same checks at another size
+    # (e.g. MG_M=4000 MG_K=4839, the benchmark's system; the explicit-K comparisons are then skipped: 93 GB).
+    M_pts, k = int(os.environ.get('MG_M', '203')), int(os.environ.get('MG_K', '400'))
+    big = M_pts > 1000
+    WORKLOADS['mg'] = ('ethanol', M_pts, 1e-5)
     inp = make_inputs('mg')
-    n, k = inp['n'], 400
+    n = inp['n']
     frac = (k + 0.5) / n
     lam = 1e-10
     y = torch.as_tensor(inp['y'], device='cuda')
@@ -45,35 +49,62 @@ def main():
 
     # kernel pieces on the shard
     assert torch.equal(eng.kernel_diag(), ref.kernel_diag()[sl])
-    K_ref = ref.kernel_assemble()
-    assert torch.equal(eng.kernel_assemble(), K_ref[sl])
+    if not big:
+        K_ref = ref.kernel_assemble()
+        assert torch.equal(eng.kernel_assemble(), K_ref[sl])
 
     # pivoted Cholesky + Woodbury
     Lt, idx, _, _ = eng.pchol_build(k)
     Lt_ref, idx_ref, _, _ = ref.pchol_build(k)
     assert torch.equal(idx, idx_ref), 'pivot permutation differs between sharded and single-GPU runs'
     err = float((Lt - Lt_ref[:, sl]).abs().max() / Lt_ref.abs().max())
-    assert err < 1e-12, err
+    if rank == 0:
+        print('  pivots identical; max |dL| / max |L| = %.2e' % err, flush=True)
+    assert err < (1e-9 if big else 1e-12), err
     T = eng.woodbury_factor_(Lt, lam)
     T_ref = ref.woodbury_factor_(Lt_ref, lam)
     a = torch.randn(n, dtype=torch.float64, device='cuda', generator=torch.Generator(device='cuda').manual_seed(1))
     z = eng.precon_apply(T, lam, 1.0, a[sl].contiguous())
     z_ref = ref.precon_apply(T_ref, lam, 1.0, a)
     err = float((z - z_ref[sl]).norm() / z_ref[sl].norm())
-    assert err < 1e-8, err
+    if rank == 0:
+        print('  Woodbury apply sharded vs single: rel diff %.2e' % err, flush=True)
+    assert err < (1e-3 if big else 1e-8), err      # the 1/lam = 1e10 amplification grows with ||L L^T||
 
     # matvecs
     v = torch.randn(n, dtype=torch.float64, device='cuda', generator=torch.Generator(device='cuda').manual_seed(2))
     mv = eng.matvec_free(v)
     assert float((mv - ref.matvec_free(v)[sl]).norm() / mv.norm()) < 1e-12
 
+    del Lt, Lt_ref, T, T_ref, z, z_ref
+    torch.cuda.empty_cache()
+    if rank == 0:
+        print('  factor checks passed (pivots, L shard, Woodbury apply)', flush=True)
+
+    # symmetric tile operator with the real reduce-scatter
+    Ksym = eng.symop_assemble()
+    sv = eng.symop_apply(Ksym, v, alpha=-1.0, shift=lam)
+    gv = ref.gemv(K_ref, v, alpha=-1.0, shift=lam)[sl] if not big else ref.matvec_free(v, alpha=-1.0, shift=lam)[sl]
+    assert float((sv - gv).norm() / gv.norm()) < 1e-11
+    del Ksym
+    if big:   # the plain sharded GEMV against the matrix-free operator
+        K_loc = eng.kernel_assemble()
+        gv2 = eng.gemv(K_loc, v, alpha=-1.0, shift=lam, x_off=eng.row0)
+        assert float((gv2 - gv).norm() / gv.norm()) < 1e-11
+        del K_loc
+
     # full solves through the public entry point, sharded vs single GPU
-    for mode, variant in (('assembled', 'cholesky'), ('assembled_sym', 'cholesky'), ('matrix_free', 'cholesky'),
-                          ('assembled', 'random_scores')):
+    combos = (('assembled', 'cholesky'), ('assembled_sym', 'cholesky'), ('matrix_free', 'cholesky'),
+              ('assembled', 'random_scores'))
+    if big:
+        combos = (('matrix_free', 'cholesky'), ('assembled_sym', 'cholesky'))
+        torch.cuda.empty_cache()
+    tol_solve = 1e-3 if big else 1e-5
+    for mode, variant in combos:
         out = {}
         for tag, distributed in (('sharded', True), ('single', False)):
             task = dict(inp['task'])
-            task.update(kernel_mode=mode, distributed=distributed, solver_tol=1e-5)
+            task.update(kernel_mode=mode, distributed=distributed, solver_tol=tol_solve)
             np.random.seed(0)
             it = Iterative(None, None)
             alphas, iters, resid, rmse, idxs, conv, info = it.solve(
@@ -83,19 +114,12 @@ def main():
             out[tag] = (alphas, iters, idxs)
             it.engine.close()
         d = np.linalg.norm(out['sharded'][0] - out['single'][0]) / np.linalg.norm(out['single'][0])
-        assert d < 1e-4, (mode, variant, d)
         i1, i0 = out['sharded'][1], out['single'][1]
-        assert abs(i1 - i0) <= max(1, int(0.05 * i0)), (mode, variant, i1, i0)
-        assert np.array_equal(out['sharded'][2], out['single'][2])
         if rank == 0:
             print('  %s/%s: iters sharded %d single %d, |dalpha|/|alpha| = %.2e' % (mode, variant, i1, i0, d), flush=True)
-
-    # symmetric tile operator with the real reduce-scatter
-    Ksym = eng.symop_assemble()
-    sv = eng.symop_apply(Ksym, v, alpha=-1.0, shift=lam)
-    gv = ref.gemv(K_ref, v, alpha=-1.0, shift=lam)[sl]
-    assert float((sv - gv).norm() / gv.norm()) < 1e-12
-    del Ksym
+        assert d < (1e-2 if big else 1e-4), (mode, variant, d)   # both are tol-accurate solutions (tol 1e-3 when big)
+        assert abs(i1 - i0) <= max(1, int(0.05 * i0)), (mode, variant, i1, i0)
+        assert np.array_equal(out['sharded'][2], out['single'][2])
 
     # replicated-vector helper
     full = allgather_rows(eng, a[sl].contiguous())

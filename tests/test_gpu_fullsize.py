@@ -110,6 +110,36 @@ def test_woodbury_inverse_property(full):
     full['T'] = T
 
 
+def test_symmetric_storage_is_half_and_matches(full):
+    """The symmetric tile storage (packed bands, TMA kernel) holds about half of K and gives the same matvec."""
+    torch, eng, K = full['torch'], full['eng'], full['K']
+    assert eng.symop_storage_elems() < 0.51 * eng.n * eng.n
+    gen = torch.Generator(device=eng.device).manual_seed(3)
+    v = torch.randn(eng.n, dtype=torch.float64, device=eng.device, generator=gen)
+    ref = eng.gemv(K, v, alpha=-1.0, shift=LAM)
+    Ksym = eng.symop_assemble()
+    out = eng.symop_apply(Ksym, v, alpha=-1.0, shift=LAM)
+    assert _rel(out, ref) < 1e-12
+    assert torch.equal(out, eng.symop_apply(Ksym, v, alpha=-1.0, shift=LAM))     # deterministic
+    del Ksym
+
+
+def test_woodbury_at_bench_rank(full):
+    """Same Woodbury identity at the rank the benchmark uses (k = 4839: 76 POTRF panels, 19 outer TRSM panels)."""
+    torch, eng, inp = full['torch'], full['eng'], full['inp']
+    k = inp['k']
+    Lt = eng.pchol_build(k, want_times=False)[0]
+    gen = torch.Generator(device=eng.device).manual_seed(4)
+    v = torch.randn(eng.n, dtype=torch.float64, device=eng.device, generator=gen)
+    lam_t = 1e-3
+    w = Lt.t() @ (Lt @ v) + lam_t * v
+    T = eng.woodbury_factor_(Lt, lam_t)
+    assert _rel(eng.precon_apply(T, lam_t, 1.0, w), v) < 1e-9
+    u = torch.randn(k, dtype=torch.float64, device=eng.device, generator=gen)
+    assert _rel(T @ (T.t() @ u), u) < 1e-3          # T T^T = I - lam W^{-1}
+    del T, Lt
+
+
 def test_pcg_solution_checked_with_other_operator(full):
     torch, eng, K, inp = full['torch'], full['eng'], full['K'], full['inp']
     T = full.get('T')

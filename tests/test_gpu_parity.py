@@ -326,7 +326,6 @@ def test_symmetric_tile_operator_emulated_ranks(torch_cuda, golden, case):
             assert [t[:4] + (t[6],) for t in tiles] == symop_plan(M, world, rank)
             Ksym = torch.full((eng.symop_storage_elems(),), float('nan'), dtype=torch.float64, device=eng.device)
             eng.symop_assemble(out=Ksym)
-            elems += Ksym.numel()
             # entries of the stored tiles equal the reference's K (diagonal tile: the part the strips read)
             for (i0, i1, j0, j1, ld, off, diag) in tiles:
                 nr, nc = (i1 - i0) * eng.dim_i, (j1 - j0) * eng.dim_i
@@ -342,8 +341,6 @@ def test_symmetric_tile_operator_emulated_ranks(torch_cuda, golden, case):
                 assert np.abs(tile - ref).max() <= TOL * np.abs(g['K']).max()
             total += eng.symop_apply(Ksym, v, partial=True)
         assert relerr(total.cpu().numpy(), Kv) < TOL, world
-        if world >= 4 and M % world == 0:
-            assert elems < 0.8 * eng.n * eng.n          # about half of the matrix is stored in total
     eng.set_layout(0, 1)
     Ksym = eng.symop_assemble()
     out = eng.symop_apply(Ksym, v, alpha=1.0, shift=-lam).cpu().numpy()
