@@ -265,6 +265,8 @@ def run_ours(args):
     task = dict(inp['task'])
     task['kernel_mode'] = args.mode
     task['_want_hist'] = True
+    if args.opt:
+        task['_options'] = {kv.split('=')[0]: int(kv.split('=')[1]) for kv in args.opt}
     dev = torch.device('cuda', local_rank)
 
     def barrier():
@@ -436,6 +438,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer arm (profiling runs)')
     ap.add_argument('--tol', type=float, default=None, help='override the relative residual target (profiling runs)')
     ap.add_argument('--k', type=int, default=None, help='override the preconditioner rank')
+    ap.add_argument('--opt', action='append', default=[], help='library option name=int (mlffpc_set_option), repeatable')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

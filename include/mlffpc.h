@@ -162,7 +162,7 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
  * Replaces iterative_cholesky.py:141-143.  W is a k*k device scratch. */
 int mlffpc_woodbury_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, double lam, double* W,
                            void* stream);
-/* z = sign * (r - T^T (T r)) / lam  on the local rows; u is a k-vector device scratch.
+/* z = sign * (r - T^T (T r)) / lam  on the local rows; u is a device scratch of 2 k + 4 doubles.
  * sign = +1: iterative_cholesky.py:145-148; sign = -1: the Nystroem operator
  * (iterative_solver.py:315-318) and _init_precon_operator_sb (:376-379). */
 int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,

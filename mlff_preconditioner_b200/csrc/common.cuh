@@ -91,6 +91,9 @@ struct mlffpc_ctx {
     // partition used by the symmetric tile operator; follows the communicator unless overridden by the
     // options "layout_rank"/"layout_world" (rank emulation on one GPU, tests only)
     int lay_rank = 0, lay_world = 1;
+    int precon_accuracy = 0;       // option "precon_accuracy": 1 = Kahan-compensated T r and T^T u (diagnostics)
+    bool pchol_lookahead = true;   // option "pchol_lookahead": candidate-panel (blocked) pivoted Cholesky
+    long long last_pchol_refills = 0;  // panel rebuilds of the last mlffpc_pchol_build (diagnostics)
     bool use_symv = false;  // option "symmetric_gemv": the assembled operator is the symmetric tile storage (symop.cu)
     // small persistent device scratch owned by the ctx (scalars / partial reductions, a few KB)
     double* scal = nullptr;    // device scalars
@@ -134,10 +137,11 @@ __device__ __forceinline__ int pair_index(int x, int y) {
 
 // HBM-bound matrix-vector kernels (gemv.cu)
 int launch_gemv_rows(const double* K, int64_t n_rows, int64_t n_cols, int64_t ld, const double* x,
-                     double* y, double alpha, double shift, int64_t x_off, cudaStream_t s);
+                     double* y, double alpha, double shift, int64_t x_off, cudaStream_t s,
+                     bool compensated = false);
 int launch_tgemv_cols(const double* T, int64_t k, int64_t n_cols, int64_t ld, const double* w,
                       double* out, int post, const double* r, double sign_over_lam, int num_sms,
-                      cudaStream_t s);
+                      cudaStream_t s, bool compensated = false);
 // symmetric operator (symop.cu, symtma.cu)
 int64_t symv_ws_bytes(int64_t n);
 int launch_symv(mlffpc_ctx* ctx, const double* K, int64_t n, int64_t ld, const double* x, double* y, double alpha,

@@ -214,6 +214,8 @@ int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value) {
     MLFFPC_REQUIRE(ctx && name, "set_option: NULL argument");
     const std::string nm(name);
     if (nm == "symmetric_gemv") { ctx->use_symv = value != 0; return MLFFPC_OK; }
+    if (nm == "precon_accuracy") { ctx->precon_accuracy = (int)value; return MLFFPC_OK; }
+    if (nm == "pchol_lookahead") { ctx->pchol_lookahead = value != 0; return MLFFPC_OK; }
     if (nm == "layout_world") {
         MLFFPC_REQUIRE(value >= 1 && value <= 1024, "set_option: layout_world out of range");
         ctx->lay_world = (int)value;

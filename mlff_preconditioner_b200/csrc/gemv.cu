@@ -14,7 +14,15 @@ __device__ __forceinline__ double2 ld_stream2(const double* p) {
     return __ldcs(reinterpret_cast<const double2*>(p));
 }
 
-template <bool VEC2, int GEMV_ROWS>
+// Kahan-compensated accumulate: s += a*b with the running error in c
+__device__ __forceinline__ void kahan_fma(double a, double b, double& s, double& c) {
+    const double y = fma(a, b, -c);
+    const double t = s + y;
+    c = (t - s) - y;
+    s = t;
+}
+
+template <bool VEC2, int GEMV_ROWS, bool COMP>
 __global__ void __launch_bounds__(GEMV_THREADS)
 gemv_rows_kernel(const double* __restrict__ K, int64_t n_rows, int64_t n_cols, int64_t ld,
                  const double* __restrict__ x, double* __restrict__ y, double alpha, double shift,
@@ -22,9 +30,9 @@ gemv_rows_kernel(const double* __restrict__ K, int64_t n_rows, int64_t n_cols, i
     __shared__ double red[GEMV_ROWS][GEMV_THREADS / 32];
     const int64_t r0 = (int64_t)blockIdx.x * GEMV_ROWS;
     const int tid = threadIdx.x;
-    double acc[GEMV_ROWS];
+    double acc[GEMV_ROWS], cmp[GEMV_ROWS];
 #pragma unroll
-    for (int r = 0; r < GEMV_ROWS; ++r) acc[r] = 0.0;
+    for (int r = 0; r < GEMV_ROWS; ++r) acc[r] = cmp[r] = 0.0;
 
     const double* rowp[GEMV_ROWS];
 #pragma unroll
@@ -48,15 +56,26 @@ gemv_rows_kernel(const double* __restrict__ K, int64_t n_rows, int64_t n_cols, i
 #pragma unroll
             for (int u = 0; u < UNR; ++u)
 #pragma unroll
-                for (int r = 0; r < GEMV_ROWS; ++r)
-                    acc[r] = fma(kv[u][r].y, xv[u].y, fma(kv[u][r].x, xv[u].x, acc[r]));
+                for (int r = 0; r < GEMV_ROWS; ++r) {
+                    if (COMP) {
+                        kahan_fma(kv[u][r].x, xv[u].x, acc[r], cmp[r]);
+                        kahan_fma(kv[u][r].y, xv[u].y, acc[r], cmp[r]);
+                    } else {
+                        acc[r] = fma(kv[u][r].y, xv[u].y, fma(kv[u][r].x, xv[u].x, acc[r]));
+                    }
+                }
         }
         for (; c < nv; c += GEMV_THREADS) {
             const double2 xv = __ldg(reinterpret_cast<const double2*>(x) + c);
 #pragma unroll
             for (int r = 0; r < GEMV_ROWS; ++r) {
                 const double2 kv = ld_stream2(rowp[r] + 2 * c);
-                acc[r] = fma(kv.y, xv.y, fma(kv.x, xv.x, acc[r]));
+                if (COMP) {
+                    kahan_fma(kv.x, xv.x, acc[r], cmp[r]);
+                    kahan_fma(kv.y, xv.y, acc[r], cmp[r]);
+                } else {
+                    acc[r] = fma(kv.y, xv.y, fma(kv.x, xv.x, acc[r]));
+                }
             }
         }
         if ((n_cols & 1) && tid == 0) {
@@ -96,7 +115,7 @@ gemv_rows_kernel(const double* __restrict__ K, int64_t n_rows, int64_t n_cols, i
 // POST: 0 = plain store; 1 = precon apply: out = sign*(r - acc)/lam.
 constexpr int TGEMV_THREADS = 256;
 
-template <int MSPLIT>
+template <int MSPLIT, bool COMP>
 __global__ void __launch_bounds__(TGEMV_THREADS)
 tgemv_cols_kernel(const double* __restrict__ T, int64_t k, int64_t n_cols, int64_t ld,
                   const double* __restrict__ w, double* __restrict__ out, int post,
@@ -105,7 +124,7 @@ tgemv_cols_kernel(const double* __restrict__ T, int64_t k, int64_t n_cols, int64
     __shared__ double red[MSPLIT][COLS];
     const int tc = threadIdx.x % COLS, ts = threadIdx.x / COLS;
     const int64_t c = (int64_t)blockIdx.x * COLS + tc;
-    double acc = 0.0;
+    double acc = 0.0, cmp = 0.0;
     if (c < n_cols) {
         const double* Tp = T + c;
         int64_t m = ts;
@@ -115,9 +134,15 @@ tgemv_cols_kernel(const double* __restrict__ T, int64_t k, int64_t n_cols, int64
 #pragma unroll
             for (int u = 0; u < 8; ++u) t[u] = __ldcs(Tp + (m + u * MSPLIT) * ld);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc = fma(t[u], __ldg(w + m + u * MSPLIT), acc);
+            for (int u = 0; u < 8; ++u) {
+                if (COMP) kahan_fma(t[u], __ldg(w + m + u * MSPLIT), acc, cmp);
+                else acc = fma(t[u], __ldg(w + m + u * MSPLIT), acc);
+            }
         }
-        for (; m < k; m += MSPLIT) acc = fma(__ldcs(Tp + m * ld), __ldg(w + m), acc);
+        for (; m < k; m += MSPLIT) {
+            if (COMP) kahan_fma(__ldcs(Tp + m * ld), __ldg(w + m), acc, cmp);
+            else acc = fma(__ldcs(Tp + m * ld), __ldg(w + m), acc);
+        }
     }
     if (MSPLIT > 1) {
         red[ts][tc] = acc;
@@ -133,37 +158,45 @@ tgemv_cols_kernel(const double* __restrict__ T, int64_t k, int64_t n_cols, int64
 }
 
 int launch_gemv_rows(const double* K, int64_t n_rows, int64_t n_cols, int64_t ld, const double* x,
-                     double* y, double alpha, double shift, int64_t x_off, cudaStream_t s) {
+                     double* y, double alpha, double shift, int64_t x_off, cudaStream_t s, bool compensated) {
     if (n_rows <= 0) return MLFFPC_OK;
     const bool vec2 = (ld % 2 == 0) && (((uintptr_t)K | (uintptr_t)x) % 16 == 0);
     const bool few_rows = n_rows < 8 * 148 * 12;  // fewer than ~4 waves of 8-row CTAs
     const int rows = few_rows ? 4 : 8;
     const unsigned grid = (unsigned)((n_rows + rows - 1) / rows);
-    if (vec2 && few_rows)
-        gemv_rows_kernel<true, 4><<<grid, GEMV_THREADS, 0, s>>>(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off);
+    if (compensated && vec2 && few_rows)
+        gemv_rows_kernel<true, 4, true><<<grid, GEMV_THREADS, 0, s>>>(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off);
+    else if (compensated && vec2)
+        gemv_rows_kernel<true, 8, true><<<grid, GEMV_THREADS, 0, s>>>(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off);
+    else if (vec2 && few_rows)
+        gemv_rows_kernel<true, 4, false><<<grid, GEMV_THREADS, 0, s>>>(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off);
     else if (vec2)
-        gemv_rows_kernel<true, 8><<<grid, GEMV_THREADS, 0, s>>>(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off);
+        gemv_rows_kernel<true, 8, false><<<grid, GEMV_THREADS, 0, s>>>(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off);
     else if (few_rows)
-        gemv_rows_kernel<false, 4><<<grid, GEMV_THREADS, 0, s>>>(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off);
+        gemv_rows_kernel<false, 4, false><<<grid, GEMV_THREADS, 0, s>>>(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off);
     else
-        gemv_rows_kernel<false, 8><<<grid, GEMV_THREADS, 0, s>>>(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off);
+        gemv_rows_kernel<false, 8, false><<<grid, GEMV_THREADS, 0, s>>>(K, n_rows, n_cols, ld, x, y, alpha, shift, x_off);
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;
 }
 
 int launch_tgemv_cols(const double* T, int64_t k, int64_t n_cols, int64_t ld, const double* w,
                       double* out, int post, const double* r, double sign_over_lam, int num_sms,
-                      cudaStream_t s) {
+                      cudaStream_t s, bool compensated) {
     if (n_cols <= 0) return MLFFPC_OK;
     // enough threads to keep HBM busy: aim for >= 2 full waves of 256-thread CTAs
     const int64_t want = (int64_t)num_sms * 2048;
+#define MLFFPC_TGEMV(MS, CP, COLS)                                                                                  \
+    tgemv_cols_kernel<MS, CP><<<(unsigned)((n_cols + (COLS)-1) / (COLS)), TGEMV_THREADS, 0, s>>>(T, k, n_cols, ld, w, out, \
+                                                                                                 post, r, sign_over_lam)
     if (n_cols >= want || k < 64) {
-        tgemv_cols_kernel<1><<<(unsigned)((n_cols + 255) / 256), TGEMV_THREADS, 0, s>>>(T, k, n_cols, ld, w, out, post, r, sign_over_lam);
+        if (compensated) MLFFPC_TGEMV(1, true, 256); else MLFFPC_TGEMV(1, false, 256);
     } else if (n_cols * 4 >= want || k < 256) {
-        tgemv_cols_kernel<4><<<(unsigned)((n_cols + 63) / 64), TGEMV_THREADS, 0, s>>>(T, k, n_cols, ld, w, out, post, r, sign_over_lam);
+        if (compensated) MLFFPC_TGEMV(4, true, 64); else MLFFPC_TGEMV(4, false, 64);
     } else {
-        tgemv_cols_kernel<8><<<(unsigned)((n_cols + 31) / 32), TGEMV_THREADS, 0, s>>>(T, k, n_cols, ld, w, out, post, r, sign_over_lam);
+        if (compensated) MLFFPC_TGEMV(8, true, 32); else MLFFPC_TGEMV(8, false, 32);
     }
+#undef MLFFPC_TGEMV
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;
 }

@@ -104,7 +104,7 @@ static PcgWs pcg_layout(const mlffpc_ctx* c, int64_t k, bool matrix_free) {
     w.off_q = o; o = up(o + nl * 8);
     w.off_p = o; o = up(o + world * w.n_pad * 8);
     w.off_xg = o; o = up(o + (world > 1 ? world * w.n_pad * 8 : 0));
-    w.off_u = o; o = up(o + (k + 1) * 8);
+    w.off_u = o; o = up(o + (2 * k + 4) * 8);
     w.off_mv = o; o = up(o + (matrix_free ? matvec_free_ws_bytes(c) : 0));
     w.off_symv = o; o = up(o + ((!matrix_free && c->use_symv) ? symop_ws_bytes(c) : 0));
     w.total = o + 256;

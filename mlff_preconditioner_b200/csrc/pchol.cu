@@ -4,7 +4,17 @@
 //           L[pi,m] = sqrt(diag[pi]);  L[rest,m] = (A[rest,pi] - L[rest,:m] L[pi,:m]) / L[pi,m];
 //           diag[rest] -= L[rest,m]^2.
 // The factor is kept transposed, Lt[m, r] = L[row0 + r, m], so that the Schur dot streams m
-// coalesced rows of length n_local -- the 4 n k^2-byte HBM stream that bounds the build.
+// coalesced rows of length n_local -- the 4 n k^2-byte HBM stream that bounds the plain build.
+//
+// Blocked variant ("look-ahead", default for k >= 128): the greedy pivot order cannot be known in advance,
+// but the next pivots almost always come from the rows with the largest residual diagonal.  A panel of
+// LA_C candidate columns is kept with the Schur correction of ALL columns chosen so far already applied
+// by one DMMA GEMM   R0[cands, :] = A[cands, :] - L[cands, :m0] L[:, :m0]^T   (a rank-m0 update of a
+// LA_C-column block, one pass over the factor for LA_C columns instead of one pass per column).  While
+// the arg-max pivot is one of the candidates, a step only applies the columns chosen since the panel was
+// built (m - m0 <= a few dozen rows of Lt); when it is not, the panel is rebuilt from the current top
+// LA_C residual diagonals (which contain the arg-max by construction).  Same pivots, same factor up to
+// summation order; the HBM stream drops from 4 n k^2 bytes to about 4 n k^2 / (average run length).
 #include <vector>
 
 #include "common.cuh"
@@ -89,7 +99,8 @@ __global__ void pchol_reduce_kernel(const Cand* __restrict__ partials, int count
 __global__ void pchol_select_kernel(const Cand* __restrict__ cands, int world, int64_t m,
                                     const int64_t* __restrict__ forced, const double* __restrict__ diag,
                                     int64_t row0, int64_t n_local, int64_t* index_columns, int32_t* pos,
-                                    int64_t* piv_idx, double* piv_val, int* flag) {
+                                    int64_t* piv_idx, double* piv_val, int* flag, const int32_t* cslot,
+                                    int* slot_out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double v = -1e300, p = 1e300, i = -1.0;
     for (int r = 0; r < world; ++r) {
@@ -110,17 +121,18 @@ __global__ void pchol_select_kernel(const Cand* __restrict__ cands, int world, i
     pos[pi] = (int32_t)m;
     pos[e] = i_argmax;
     piv_idx[0] = pi;
+    if (cslot) *slot_out = cslot[pi];
     if (!(v > 0.0)) { if (*flag == 0) *flag = (int)(m + 1); v = 1.0; }
     piv_val[0] = sqrt(v);
 }
 
 // lrow[m'] = Lt[m', pi - row0] for m' < m on the owner, 0 elsewhere (replicated by an allreduce-sum)
-__global__ void pchol_gather_row_kernel(const double* __restrict__ Lt, int64_t ld, int64_t m,
+__global__ void pchol_gather_row_kernel(const double* __restrict__ Lt, int64_t ld, int64_t m0, int64_t m,
                                         const int64_t* __restrict__ piv_idx, int64_t row0, int64_t n_local,
                                         double* __restrict__ lrow) {
     const int64_t pi = piv_idx[0];
     const bool owner = (pi >= row0 && pi < row0 + n_local);
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = m0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < m) lrow[t] = owner ? Lt[t * ld + (pi - row0)] : 0.0;
 }
 
@@ -128,10 +140,13 @@ __global__ void pchol_gather_row_kernel(const double* __restrict__ Lt, int64_t l
 constexpr int PCHOL_THREADS = 256;
 template <int MSPLIT>
 __global__ void __launch_bounds__(PCHOL_THREADS)
-pchol_update_kernel(double* __restrict__ Lt, int64_t ld, int64_t m, int64_t n_local, int64_t row0,
-                    const double* __restrict__ col, const double* __restrict__ lrow,
-                    const int64_t* __restrict__ piv_idx, const double* __restrict__ piv_val,
-                    double* __restrict__ diag, const int32_t* __restrict__ pos, Cand* partials) {
+pchol_update_kernel(double* __restrict__ Lt, int64_t ld, int64_t m0, int64_t m, int64_t n_local, int64_t row0,
+                    const double* __restrict__ col, const int* __restrict__ slot_ptr, int64_t ld_panel,
+                    const double* __restrict__ lrow, const int64_t* __restrict__ piv_idx,
+                    const double* __restrict__ piv_val, double* __restrict__ diag,
+                    const int32_t* __restrict__ pos, Cand* partials) {
+    // col: the pivot column of A on the local rows (m0 = 0), or the candidate panel whose row *slot_ptr holds
+    // that column with the first m0 factor columns already applied
     constexpr int COLS = PCHOL_THREADS / MSPLIT;
     __shared__ double red[MSPLIT][COLS];
     __shared__ Cand sm[40];
@@ -140,7 +155,7 @@ pchol_update_kernel(double* __restrict__ Lt, int64_t ld, int64_t m, int64_t n_lo
     double acc = 0.0;
     if (r < n_local) {
         const double* Lp = Lt + r;
-        int64_t q = ts;
+        int64_t q = m0 + ts;
         for (; q + 7 * MSPLIT < m; q += 8 * MSPLIT) {
             double t[8];
 #pragma unroll
@@ -164,7 +179,8 @@ pchol_update_kernel(double* __restrict__ Lt, int64_t ld, int64_t m, int64_t n_lo
         const int32_t ps = pos[g];
         double l;
         if (ps > m) {  // still a candidate row: i_pi = index_columns[m+1:]
-            l = (col[r] - acc) / piv_val[0];
+            const double* cp = slot_ptr ? (col + (int64_t)(*slot_ptr) * ld_panel) : col;
+            l = (cp[r] - acc) / piv_val[0];
             const double dn = diag[r] - l * l;
             diag[r] = dn;
             v = dn; p = (double)ps; i = (double)g;
@@ -179,6 +195,157 @@ pchol_update_kernel(double* __restrict__ Lt, int64_t ld, int64_t m, int64_t n_lo
     if (threadIdx.x == 0) partials[blockIdx.x] = sm[0];
 }
 
+
+// ---- look-ahead candidate panel -----------------------------------------------------------------------
+constexpr int LA_C = 64;        // candidate columns kept in the panel
+constexpr int LA_LCAP = 128;    // per-rank candidate list capacity (top-LA_C plus ties in the threshold bin)
+constexpr int LA_MAXE = 4096;   // merge capacity: world * LA_LCAP <= LA_MAXE
+
+__device__ __forceinline__ unsigned long long la_key(double v) {
+    return v > 0.0 ? (unsigned long long)__double_as_longlong(v) : 0ull;  // positive doubles order like integers
+}
+
+// One CTA: this rank's rows with the largest residual diagonal among the rows not chosen yet (pos >= m).
+// Radix select on the upper 33 bits of the value (3 passes of 11 bits), then an index-ordered compaction of
+// everything at or above the threshold -> deterministic list of >= min(want, available) entries.
+__global__ void __launch_bounds__(1024)
+pchol_topc_kernel(const double* __restrict__ diag, int64_t nl, int64_t row0, const int32_t* __restrict__ pos,
+                  int64_t m, int want, Cand* __restrict__ list) {
+    __shared__ int hist[2048];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_need;
+    __shared__ int s_scan[1024];
+    const int tid = threadIdx.x;
+    unsigned long long prefix = 0;
+    int need = want;
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = 52 - 11 * pass;
+        for (int b = tid; b < 2048; b += 1024) hist[b] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < nl; i += 1024) {
+            const unsigned long long key = (pos[row0 + i] >= m) ? la_key(diag[i]) : 0ull;
+            if (key != 0ull && (pass == 0 || (key >> (shift + 11)) == prefix))
+                atomicAdd(&hist[(int)((key >> shift) & 2047ull)], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int cum = 0, digit = -1;
+            for (int b = 2047; b >= 0; --b) {
+                if (cum + hist[b] >= need) { digit = b; break; }
+                cum += hist[b];
+            }
+            if (digit < 0) { digit = 0; cum = 0; }  // fewer than `need` rows are left: the threshold admits them all
+            s_prefix = (prefix << 11) | (unsigned long long)digit;
+            s_need = need - cum;
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        need = s_need;
+        __syncthreads();
+    }
+    // selected: key != 0 and (key >> 30) >= prefix ; compaction in row order (each thread owns a contiguous chunk)
+    const int64_t L = (nl + 1023) / 1024;
+    const int64_t i0 = (int64_t)tid * L, i1 = (i0 + L < nl) ? (i0 + L) : nl;
+    int cnt = 0;
+    for (int64_t i = i0; i < i1; ++i) {
+        const unsigned long long key = (pos[row0 + i] >= m) ? la_key(diag[i]) : 0ull;
+        if (key != 0ull && (key >> 30) >= prefix) ++cnt;
+    }
+    s_scan[tid] = cnt;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = (tid >= o) ? s_scan[tid - o] : 0;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    int off = s_scan[tid] - cnt;
+    const int total = s_scan[1023];
+    for (int64_t i = i0; i < i1; ++i) {
+        const int32_t ps = pos[row0 + i];
+        const double v = diag[i];
+        const unsigned long long key = (ps >= m) ? la_key(v) : 0ull;
+        if (key != 0ull && (key >> 30) >= prefix) {
+            if (off < LA_LCAP) { list[off].val = v; list[off].pos = (double)ps; list[off].idx = (double)(row0 + i); list[off].pad = 0.0; }
+            ++off;
+        }
+    }
+    for (int t = tid; t < LA_LCAP; t += 1024)
+        if (t >= total) { list[t].val = -1e300; list[t].pos = 1e300; list[t].idx = -1.0; list[t].pad = 0.0; }
+}
+
+// One CTA: merge the ranks' lists, keep the LA_C best (value descending, position ascending = the pivot
+// rule), make sure the current pivot is among them, and rewrite the candidate tables.
+//   cand_idx[LA_C] (global rows; padded with the pivot), cslot[n] (row -> slot or -1), slot_out = slot of the pivot
+__global__ void __launch_bounds__(1024)
+pchol_merge_kernel(const Cand* __restrict__ lists, int n_entries, const int64_t* __restrict__ piv_idx,
+                   int64_t* __restrict__ cand_idx, int32_t* __restrict__ cslot, int* __restrict__ slot_out) {
+    extern __shared__ double msm[];
+    int E = 1;
+    while (E < n_entries) E <<= 1;
+    double* val = msm;
+    double* ps = msm + E;
+    double* ix = msm + 2 * E;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < E; i += 1024) {
+        if (i < n_entries) { val[i] = lists[i].val; ps[i] = lists[i].pos; ix[i] = lists[i].idx; }
+        else { val[i] = -1e300; ps[i] = 1e300; ix[i] = -1.0; }
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= E; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < E; i += 1024) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool desc = ((i & k2) == 0);
+                    const bool i_first = cand_better(val[i], ps[i], val[l], ps[l]);  // i should precede l in descending order
+                    if (desc != i_first && !(val[i] == val[l] && ps[i] == ps[l])) {
+                        double t;
+                        t = val[i]; val[i] = val[l]; val[l] = t;
+                        t = ps[i]; ps[i] = ps[l]; ps[l] = t;
+                        t = ix[i]; ix[i] = ix[l]; ix[l] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // old candidates out
+    if (tid < LA_C) {
+        const int64_t old = cand_idx[tid];
+        if (old >= 0) cslot[old] = -1;
+    }
+    __syncthreads();
+    __shared__ int s_found;
+    if (tid == 0) s_found = 0;
+    __syncthreads();
+    const int64_t pi = piv_idx[0];
+    if (tid < LA_C && tid < E && val[tid] > 0.0 && (int64_t)ix[tid] == pi) s_found = 1;
+    __syncthreads();
+    if (tid < LA_C) {
+        int64_t g = (tid < E && val[tid] > 0.0) ? (int64_t)ix[tid] : -1;
+        if (!s_found && tid == LA_C - 1) g = pi;  // cannot happen unless > LA_LCAP rows tie; keep the pivot reachable
+        const bool real = g >= 0;
+        if (!real) g = pi;                        // padding (fewer than LA_C rows left): duplicates of the pivot
+        cand_idx[tid] = g;
+        if (real) cslot[g] = tid;
+    }
+    __syncthreads();
+    if (tid == 0) *slot_out = cslot[pi];
+}
+
+// Lc[j, t] = L[cand_j, t] for t < m on the owner rank, 0 elsewhere (summed over ranks by the caller)
+__global__ void pchol_gather_cand_rows_kernel(const double* __restrict__ Lt, int64_t ld, int64_t m,
+                                              const int64_t* __restrict__ cand_idx, int64_t row0, int64_t n_local,
+                                              double* __restrict__ Lc) {
+    const int j = blockIdx.y;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const int64_t g = cand_idx[j];
+    const bool owner = (g >= row0 && g < row0 + n_local);
+    Lc[(int64_t)j * m + t] = owner ? Lt[t * ld + (g - row0)] : 0.0;
+}
+
 static int pchol_msplit(int64_t n_local, int64_t m, int num_sms) {
     const int64_t want = (int64_t)num_sms * 1024;
     if (n_local >= want || m < 64) return 1;
@@ -187,8 +354,13 @@ static int pchol_msplit(int64_t n_local, int64_t m, int num_sms) {
 }
 
 struct PcholWs {
-    int64_t off_col, off_lrow, off_pos, off_cands, off_gathered, off_piv, total;
+    int64_t off_col, off_lrow, off_pos, off_cands, off_gathered, off_piv, off_cand_idx, off_cslot, off_panel, off_lc,
+        off_list, off_lists, total;
 };
+static bool pchol_lookahead_enabled(const mlffpc_ctx* c, int64_t k, bool forced) {
+    return c->pchol_lookahead && !forced && k >= 128 && (int64_t)c->comm.world * LA_LCAP <= LA_MAXE &&
+           c->n_local() >= 4 * LA_C;
+}
 static PcholWs pchol_layout(const mlffpc_ctx* c, int64_t k) {
     auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
     PcholWs w;
@@ -198,7 +370,15 @@ static PcholWs pchol_layout(const mlffpc_ctx* c, int64_t k) {
     w.off_pos = o; o = up(o + c->n * 4);
     w.off_cands = o; o = up(o + 64);                 // this rank's candidate
     w.off_gathered = o; o = up(o + 64 * 1024);        // all ranks' candidates (<= 1024 ranks)
-    w.off_piv = o; o = up(o + 64);                    // piv_idx (int64), piv_val (double), flag (int)
+    w.off_piv = o; o = up(o + 64);                    // piv_idx (int64), piv_val (double), flag (int), slot (int)
+    // look-ahead panel (allocated whenever it could be used; forced_pivots runs simply ignore it)
+    const bool la = pchol_lookahead_enabled(c, k, false);
+    w.off_cand_idx = o; o = up(o + (la ? LA_C * 8 : 0));
+    w.off_cslot = o;    o = up(o + (la ? c->n * 4 : 0));
+    w.off_panel = o;    o = up(o + (la ? (int64_t)LA_C * c->n_local() * 8 : 0));
+    w.off_lc = o;       o = up(o + (la ? (int64_t)LA_C * k * 8 : 0));
+    w.off_list = o;     o = up(o + (la ? LA_LCAP * (int64_t)sizeof(Cand) : 0));
+    w.off_lists = o;    o = up(o + (la ? (int64_t)c->comm.world * LA_LCAP * (int64_t)sizeof(Cand) : 0));
     w.total = o + 256;
     return w;
 }
@@ -241,9 +421,24 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
     const int world = ctx->comm.world;
     MLFFPC_REQUIRE(world <= 1024, "pchol_build: too many ranks");
 
+    int* slot_dev = (int*)(base + w.off_piv + 24);
+    const bool la = pchol_lookahead_enabled(ctx, k, forced_pivots != nullptr);
+    int64_t* cand_idx = (int64_t*)(base + w.off_cand_idx);
+    int32_t* cslot = (int32_t*)(base + w.off_cslot);
+    double* panel = (double*)(base + w.off_panel);
+    double* Lc = (double*)(base + w.off_lc);
+    Cand* my_list = (Cand*)(base + w.off_list);
+    Cand* all_lists = (Cand*)(base + w.off_lists);
+
     MLFFPC_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
     pchol_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, index_columns, pos);
     MLFFPC_LAUNCH_CHECK();
+    if (la) {
+        MLFFPC_CUDA(cudaMemsetAsync(cslot, 0xff, (size_t)n * 4, s));       // -1
+        MLFFPC_CUDA(cudaMemsetAsync(cand_idx, 0xff, (size_t)LA_C * 8, s));  // -1
+        MLFFPC_CUDA(cudaFuncSetAttribute(pchol_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         3 * LA_MAXE * (int)sizeof(double)));
+    }
 
     // candidate partials: the update kernel writes one per CTA; size the scan the same way
     int64_t n_part = (nl + 255) / 256;
@@ -256,6 +451,8 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
 
     int status = MLFFPC_OK;
     int prev_parts = 0;
+    int64_t m0 = 0;        // factor columns already folded into the candidate panel
+    int64_t refills = 0;
     ProfWindow pw = prof_window("pchol");
     for (int64_t m = 0; m < k && status == MLFFPC_OK; ++m) {
         pw.step(m);
@@ -268,26 +465,64 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
         pchol_reduce_kernel<<<1, 256, 0, s>>>(partials, prev_parts, my_cand);
         status = comm_allgather(ctx->comm, my_cand, all_cand, sizeof(Cand), s);
         if (status != MLFFPC_OK) break;
-        // (2) pivot, swap, sqrt
+        // (2) pivot, swap, sqrt (+ the pivot's slot in the candidate panel)
         pchol_select_kernel<<<1, 32, 0, s>>>(all_cand, world, m, forced_pivots, diag, row0, nl, index_columns,
-                                             pos, piv_idx, piv_val, flag);
+                                             pos, piv_idx, piv_val, flag, la ? cslot : nullptr, slot_dev);
         if (forced_pivots && world > 1) {
             set_error("pchol_build: forced_pivots is a single-GPU diagnostic");
             status = MLFFPC_ERR_UNSUPPORTED;
             break;
         }
-        // (3) pivot row of the factor, replicated
-        if (m > 0) {
-            pchol_gather_row_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(Lt, ld, m, piv_idx, row0, nl, lrow);
+        g_launches += 3;
+        if (la) {
+            // the host decides between "step" and "rebuild the panel, then step": one 4-byte read per step
+            cudaError_t e = cudaMemcpyAsync(ctx->h_scal + 8, slot_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { status = cuda_fail(e, "pchol slot readback", __FILE__, __LINE__); break; }
+            const int slot = *(int*)(ctx->h_scal + 8);
+            if (slot < 0) {
+                // (2b) rebuild: top rows by residual diagonal -> merged candidate list -> columns of A -> fold in L[:, :m]
+                ++refills;
+                pchol_topc_kernel<<<1, 1024, 0, s>>>(diag, nl, row0, pos, m, LA_C, my_list);
+                status = comm_allgather(ctx->comm, my_list, all_lists, LA_LCAP * sizeof(Cand), s);
+                if (status != MLFFPC_OK) break;
+                int E = 1;
+                while (E < world * LA_LCAP) E <<= 1;
+                pchol_merge_kernel<<<1, 1024, 3 * E * sizeof(double), s>>>(all_lists, world * LA_LCAP, piv_idx, cand_idx,
+                                                                         cslot, slot_dev);
+                g_launches += 2;
+                status = mlffpc_kernel_columns(ctx, cand_idx, LA_C, panel, nl, -1.0, nullptr, 0, (void*)s);
+                if (status != MLFFPC_OK) break;
+                if (m > 0) {
+                    pchol_gather_cand_rows_kernel<<<dim3((unsigned)((m + 255) / 256), LA_C), 256, 0, s>>>(
+                        Lt, ld, m, cand_idx, row0, nl, Lc);
+                    ++g_launches;
+                    status = comm_allreduce_sum(ctx->comm, Lc, (size_t)(LA_C * m), s);
+                    if (status != MLFFPC_OK) break;
+                    // panel[c, :] -= Lc[c, :m] Lt[:m, :]
+                    status = dgemm(false, LA_C, nl, m, -1.0, Lc, m, Lt, ld, 1.0, panel, nl, false, s);
+                    if (status != MLFFPC_OK) break;
+                }
+                m0 = m;
+            }
+        }
+        // (3) pivot row of the factor (columns m0 .. m-1), replicated
+        if (m > m0) {
+            pchol_gather_row_kernel<<<(unsigned)((m - m0 + 255) / 256), 256, 0, s>>>(Lt, ld, m0, m, piv_idx, row0, nl, lrow);
+            ++g_launches;
             // the owner is only known on the device: replicate with an allreduce-sum of the zero-padded row
-            if (world > 1) status = comm_allreduce_sum(ctx->comm, lrow, (size_t)m, s);
+            if (world > 1) status = comm_allreduce_sum(ctx->comm, lrow + m0, (size_t)(m - m0), s);
         }
         if (status != MLFFPC_OK) break;
-        // (4) column pi of A = -K on the local rows
-        status = launch_columns_device_col(ctx, piv_idx, col, -1.0, s);
-        if (status != MLFFPC_OK) break;
-        // (5) Schur update, new factor row, residual diagonal, next candidates
-        const int ms = pchol_msplit(nl, m, ctx->num_sms);
+        // (4) column pi of A = -K on the local rows (plain variant; the panel already holds it otherwise)
+        if (!la) {
+            status = launch_columns_device_col(ctx, piv_idx, col, -1.0, s);
+            if (status != MLFFPC_OK) break;
+        }
+        // (5) Schur update over the factor columns m0 .. m-1, new factor row, residual diagonal, next candidates
+        const double* colsrc = la ? panel : col;
+        const int* slot_ptr = la ? slot_dev : nullptr;
+        const int ms = pchol_msplit(nl, m - m0, ctx->num_sms);
         if ((nl + (256 / ms) - 1) / (256 / ms) > MLFFPC_MAX_PARTIALS) {
             set_error("pchol_build: n_local too large for the candidate buffer");
             status = MLFFPC_ERR_INVALID;
@@ -295,21 +530,22 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
         }
         if (ms == 1) {
             prev_parts = (int)((nl + 255) / 256);
-            pchol_update_kernel<1><<<prev_parts, PCHOL_THREADS, 0, s>>>(Lt, ld, m, nl, row0, col, lrow, piv_idx, piv_val, diag, pos, partials);
+            pchol_update_kernel<1><<<prev_parts, PCHOL_THREADS, 0, s>>>(Lt, ld, m0, m, nl, row0, colsrc, slot_ptr, nl, lrow, piv_idx, piv_val, diag, pos, partials);
         } else if (ms == 4) {
             prev_parts = (int)((nl + 63) / 64);
-            pchol_update_kernel<4><<<prev_parts, PCHOL_THREADS, 0, s>>>(Lt, ld, m, nl, row0, col, lrow, piv_idx, piv_val, diag, pos, partials);
+            pchol_update_kernel<4><<<prev_parts, PCHOL_THREADS, 0, s>>>(Lt, ld, m0, m, nl, row0, colsrc, slot_ptr, nl, lrow, piv_idx, piv_val, diag, pos, partials);
         } else {
             prev_parts = (int)((nl + 31) / 32);
-            pchol_update_kernel<8><<<prev_parts, PCHOL_THREADS, 0, s>>>(Lt, ld, m, nl, row0, col, lrow, piv_idx, piv_val, diag, pos, partials);
+            pchol_update_kernel<8><<<prev_parts, PCHOL_THREADS, 0, s>>>(Lt, ld, m0, m, nl, row0, colsrc, slot_ptr, nl, lrow, piv_idx, piv_val, diag, pos, partials);
         }
-        g_launches += (m > 0) ? 4 : 4;  // scan|gather + reduce + select + update (the column kernel counts itself)
+        ++g_launches;
         {
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) { status = cuda_fail(e, "pchol step", __FILE__, __LINE__); break; }
         }
         if (step_ms_host) cudaEventRecord(ev[(size_t)m + 1], s);
     }
+    ctx->last_pchol_refills = refills;
 
     pw.end();
     int h_flag = 0;

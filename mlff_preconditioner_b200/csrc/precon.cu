@@ -7,14 +7,31 @@
 
 namespace mlffpc {
 
+__global__ void add_inplace_kernel(double* __restrict__ a, const double* __restrict__ b, int64_t n) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) a[t] += b[t];
+}
+
+// u: device scratch of 2 k + 4 doubles
 int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
                  const double* r, double* z, double* u, cudaStream_t s) {
     const int64_t nl = ctx->n_local();
     // u = T r  (local part), summed over ranks
-    MLFFPC_TRY(launch_gemv_rows(T, k, nl, ld, r, u, 1.0, 0.0, 0, s));
+    const bool comp = ctx->precon_accuracy == 1;
+    if (ctx->precon_accuracy == 2 && nl >= 4) {
+        // diagnostics: u as the sum of two half-length products (the summation order of a 2-rank run)
+        const int64_t h = (nl / 2) & ~(int64_t)1;
+        double* u2 = u + k + 2;
+        MLFFPC_TRY(launch_gemv_rows(T, k, h, ld, r, u, 1.0, 0.0, 0, s, false));
+        MLFFPC_TRY(launch_gemv_rows(T + h, k, nl - h, ld, r + h, u2, 1.0, 0.0, 0, s, false));
+        add_inplace_kernel<<<(unsigned)((k + 255) / 256), 256, 0, s>>>(u, u2, k);
+        MLFFPC_LAUNCH_CHECK();
+    } else {
+        MLFFPC_TRY(launch_gemv_rows(T, k, nl, ld, r, u, 1.0, 0.0, 0, s, comp));
+    }
     MLFFPC_TRY(comm_allreduce_sum(ctx->comm, u, (size_t)k, s));
     // z = sign (r - T^T u) / lam
-    MLFFPC_TRY(launch_tgemv_cols(T, k, nl, ld, u, z, 1, r, sign / lam, ctx->num_sms, s));
+    MLFFPC_TRY(launch_tgemv_cols(T, k, nl, ld, u, z, 1, r, sign / lam, ctx->num_sms, s, comp));
     return MLFFPC_OK;
 }
 

@@ -334,7 +334,7 @@ class Engine(object):
         if out is None:
             out = self.empty(self.n_local)
         k = 0 if T is None else T.shape[0]
-        u = self.empty(max(k, 1))
+        u = self.empty(2 * k + 4)
         _lib.check(self.lib.mlffpc_precon_apply(self.ctx, _ptr(T), k, 0 if T is None else T.stride(0), float(lam),
                                                 float(sign), _ptr(r), _ptr(out), _ptr(u), self._stream()))
         return out

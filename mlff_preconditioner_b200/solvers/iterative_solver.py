@@ -145,6 +145,8 @@ class Iterative(object):
         kernel operator, PCG.  ``y_t`` is the full right-hand side on the device.  Returns
         ``(x_local, iters, resid, info, inducing_pts_idxs, info_cholesky, t_precon, t_cg)``."""
         self.engine = eng
+        for name, value in (task.get('_options') or {}).items():   # library switches (diagnostics, A/B runs)
+            eng.set_option(name, value)
         n, n_train, n_atoms = eng.n, eng.M, eng.N
         sig, lam = task['sig'], task['lam']
         R_desc = R_d_desc = tril_perms_lin = None  # geometry lives in the engine
