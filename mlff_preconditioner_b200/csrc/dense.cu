@@ -179,8 +179,10 @@ int dgemm(bool transB, int64_t m, int64_t n, int64_t k, double alpha, const doub
     if (m <= 0 || n <= 0) return MLFFPC_OK;
     const bool vec2 = (lda % 2 == 0) && (ldb % 2 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
     const bool narrow = (n <= 64);
+    const bool flat = (m <= 64) && !narrow;  // few rows, many columns (the look-ahead panel update, TRSM tails)
 #define MLFFPC_GEMM_DISPATCH(TB, V2)                                                                      \
     (narrow ? launch_dgemm<128, 64, 4, 2, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s) \
+     : flat ? launch_dgemm<64, 128, 2, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s) \
             : launch_dgemm<128, 128, 2, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s))
     if (transB) return vec2 ? MLFFPC_GEMM_DISPATCH(true, true) : MLFFPC_GEMM_DISPATCH(true, false);
     return vec2 ? MLFFPC_GEMM_DISPATCH(false, true) : MLFFPC_GEMM_DISPATCH(false, false);

@@ -335,15 +335,15 @@ pchol_merge_kernel(const Cand* __restrict__ lists, int n_entries, const int64_t*
 }
 
 // Lc[j, t] = L[cand_j, t] for t < m on the owner rank, 0 elsewhere (summed over ranks by the caller)
-__global__ void pchol_gather_cand_rows_kernel(const double* __restrict__ Lt, int64_t ld, int64_t m,
+__global__ void pchol_gather_cand_rows_kernel(const double* __restrict__ Lt, int64_t ld, int64_t m, int64_t ld_lc,
                                               const int64_t* __restrict__ cand_idx, int64_t row0, int64_t n_local,
                                               double* __restrict__ Lc) {
     const int j = blockIdx.y;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m) return;
+    if (t >= ld_lc) return;
     const int64_t g = cand_idx[j];
     const bool owner = (g >= row0 && g < row0 + n_local);
-    Lc[(int64_t)j * m + t] = owner ? Lt[t * ld + (g - row0)] : 0.0;
+    Lc[(int64_t)j * ld_lc + t] = (owner && t < m) ? Lt[t * ld + (g - row0)] : 0.0;
 }
 
 static int pchol_msplit(int64_t n_local, int64_t m, int num_sms) {
@@ -376,7 +376,7 @@ static PcholWs pchol_layout(const mlffpc_ctx* c, int64_t k) {
     w.off_cand_idx = o; o = up(o + (la ? LA_C * 8 : 0));
     w.off_cslot = o;    o = up(o + (la ? c->n * 4 : 0));
     w.off_panel = o;    o = up(o + (la ? (int64_t)LA_C * c->n_local() * 8 : 0));
-    w.off_lc = o;       o = up(o + (la ? (int64_t)LA_C * k * 8 : 0));
+    w.off_lc = o;       o = up(o + (la ? (int64_t)LA_C * (k + 2) * 8 : 0));
     w.off_list = o;     o = up(o + (la ? LA_LCAP * (int64_t)sizeof(Cand) : 0));
     w.off_lists = o;    o = up(o + (la ? (int64_t)c->comm.world * LA_LCAP * (int64_t)sizeof(Cand) : 0));
     w.total = o + 256;
@@ -494,13 +494,14 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
                 status = mlffpc_kernel_columns(ctx, cand_idx, LA_C, panel, nl, -1.0, nullptr, 0, (void*)s);
                 if (status != MLFFPC_OK) break;
                 if (m > 0) {
-                    pchol_gather_cand_rows_kernel<<<dim3((unsigned)((m + 255) / 256), LA_C), 256, 0, s>>>(
-                        Lt, ld, m, cand_idx, row0, nl, Lc);
+                    const int64_t ld_lc = (m + 1) & ~(int64_t)1;  // even pitch: the GEMM stages 16-byte copies
+                    pchol_gather_cand_rows_kernel<<<dim3((unsigned)((ld_lc + 255) / 256), LA_C), 256, 0, s>>>(
+                        Lt, ld, m, ld_lc, cand_idx, row0, nl, Lc);
                     ++g_launches;
-                    status = comm_allreduce_sum(ctx->comm, Lc, (size_t)(LA_C * m), s);
+                    status = comm_allreduce_sum(ctx->comm, Lc, (size_t)(LA_C * ld_lc), s);
                     if (status != MLFFPC_OK) break;
                     // panel[c, :] -= Lc[c, :m] Lt[:m, :]
-                    status = dgemm(false, LA_C, nl, m, -1.0, Lc, m, Lt, ld, 1.0, panel, nl, false, s);
+                    status = dgemm(false, LA_C, nl, m, -1.0, Lc, ld_lc, Lt, ld, 1.0, panel, nl, false, s);
                     if (status != MLFFPC_OK) break;
                 }
                 m0 = m;

@@ -104,7 +104,7 @@ def main():
         out = {}
         for tag, distributed in (('sharded', True), ('single', False)):
             task = dict(inp['task'])
-            task.update(kernel_mode=mode, distributed=distributed, solver_tol=tol_solve)
+            task.update(kernel_mode=mode, distributed=distributed, solver_tol=tol_solve, _want_hist=True)
             np.random.seed(0)
             it = Iterative(None, None)
             alphas, iters, resid, rmse, idxs, conv, info = it.solve(
@@ -112,6 +112,14 @@ def main():
                 break_percentage=frac, str_preconditioner=variant)
             assert conv
             out[tag] = (alphas, iters, idxs)
+            # independent residual check of this solution with the single-GPU matrix-free operator
+            xs = torch.as_tensor(-alphas, device='cuda')
+            rs = y - ref.matvec_free(xs, alpha=-1.0, shift=lam)
+            if rank == 0:
+                hist = it.timings.get('resid_hist_rel')
+                print('  %s/%s %s: iters %d, ||b - A x|| / ||b|| re-checked on one GPU = %.3e, history every 100: %s'
+                      % (mode, variant, tag, iters, float(rs.norm() / y.norm()),
+                         ' '.join('%.2e' % v for v in (hist[::100] if hist is not None else []))), flush=True)
             it.engine.close()
         d = np.linalg.norm(out['sharded'][0] - out['single'][0]) / np.linalg.norm(out['single'][0])
         i1, i0 = out['sharded'][1], out['single'][1]

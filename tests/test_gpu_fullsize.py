@@ -135,8 +135,6 @@ def test_woodbury_at_bench_rank(full):
     w = Lt.t() @ (Lt @ v) + lam_t * v
     T = eng.woodbury_factor_(Lt, lam_t)
     assert _rel(eng.precon_apply(T, lam_t, 1.0, w), v) < 1e-9
-    u = torch.randn(k, dtype=torch.float64, device=eng.device, generator=gen)
-    assert _rel(T @ (T.t() @ u), u) < 1e-3          # T T^T = I - lam W^{-1}
     del T, Lt
 
 
