@@ -265,6 +265,8 @@ def run_ours(args):
     task = dict(inp['task'])
     task['kernel_mode'] = args.mode
     task['_want_hist'] = True
+    if args.precon_form:
+        task['precon_form'] = args.precon_form
     if args.opt:
         task['_options'] = {kv.split('=')[0]: int(kv.split('=')[1]) for kv in args.opt}
     dev = torch.device('cuda', local_rank)
@@ -344,7 +346,7 @@ def run_ours(args):
         entries = symop_entries_read(symop_plan(eng.M, world, rank), eng.dim_i)
         alg_bytes = 8.0 * entries + 8.0 * eng.n + 8.0 * eng.n_local
         achieved = alg_bytes / avg_op_s / 1e9
-        roofline = {'bound': 'hbm', 'kernel': 'symv_tile_kernel (+ symv_reduce_kernel)', 'achieved': achieved,
+        roofline = {'bound': 'hbm', 'kernel': 'symv_tma_kernel (+ symv_tma_reduce_kernel)', 'achieved': achieved,
                     'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
                     'bytes_per_launch': alg_bytes, 'avg_launch_ms': avg_op_s * 1e3, 'launches_timed': op_calls,
                     'note': 'symmetric storage: every entry of the lower block triangle is read once and used for '
@@ -357,6 +359,15 @@ def run_ours(args):
                     'peak': 40.0, 'unit': 'TFLOP/s', 'frac': flops / avg_op_s / 1e12 / 40.0, 'traffic': None,
                     'peak_source': 'nominal B200 fp64 (no measured fp64 peak in MEASURED_PEAKS.json)',
                     'avg_launch_ms': avg_op_s * 1e3, 'launches_timed': op_calls}
+    # measured DRAM traffic of the dominant kernel (ncu --set full), only valid for the configuration it was captured on
+    if args.workload == 'cfg2' and world == 1 and not args.M:
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(args.mode)
+            if tr:
+                roofline['traffic'] = tr['bytes']
+                roofline['traffic_source'] = tr['source']
+        except Exception:
+            pass
     phases = {'preconditioner_s': tm['preconditioner'], 'pchol_build_s': tm.get('pchol_build'),
               'assemble_s': tm['assemble'], 'cg_s': tm['cg'], 'cg_iters': iters, 'resid': resid,
               'rel_resid': resid / np.linalg.norm(inp['y']), 'converged': info == 0,
@@ -438,6 +449,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer arm (profiling runs)')
     ap.add_argument('--tol', type=float, default=None, help='override the relative residual target (profiling runs)')
     ap.add_argument('--k', type=int, default=None, help='override the preconditioner rank')
+    ap.add_argument('--precon-form', default=None, choices=['orthonormal', 'woodbury'])
     ap.add_argument('--opt', action='append', default=[], help='library option name=int (mlffpc_set_option), repeatable')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -162,17 +162,28 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
  * Replaces iterative_cholesky.py:141-143.  W is a k*k device scratch. */
 int mlffpc_woodbury_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, double lam, double* W,
                            void* stream);
-/* z = sign * (r - T^T (T r)) / lam  on the local rows; u is a device scratch of 2 k + 4 doubles.
+/* The same inverse (L L^T + lam I)^{-1} in an orthonormal basis, in place: Lt -> Qt [k, n_local] with
+ * Qt Qt^T = I (CholeskyQR2 of L, two SYRK + POTRF + TRSM passes) and Mk[k,k] = (Qt L L^T Qt^T + lam I)^{-1}.
+ * The Woodbury form above subtracts T^T T r from r with lam = 1e-10 in the denominator: rounding in the k x k
+ * Gram of 1e5-long columns (~1e-13 |W|) is then a visible perturbation of the operator and CG stalls on a
+ * plateau (DESIGN.md "Woodbury accuracy"); this form evaluates the range part without cancellation.  Same
+ * operator, same traffic per apply.  W1, W2: k*k device scratch each. */
+int mlffpc_orthonormal_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, double lam, double* Mk,
+                              double* W1, double* W2, void* stream);
+/* z = sign * (r - T^T (T r)) / lam  on the local rows (Mk == NULL), or with Mk from
+ * mlffpc_orthonormal_factor  z = sign * ((r - T^T (T r)) / lam + T^T Mk (T r)).
+ * u is a device scratch of 2 k + 4 doubles.
  * sign = +1: iterative_cholesky.py:145-148; sign = -1: the Nystroem operator
  * (iterative_solver.py:315-318) and _init_precon_operator_sb (:376-379). */
 int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
-                        const double* r, double* z, double* u, void* stream);
+                        const double* r, double* z, double* u, const double* Mk, void* stream);
 
 /* ---------------------------------------------------------------- PCG ---- */
 /* Preconditioned CG on A x = b, A = -K + lam I, with scipy-1.7.3 legacy stopping semantics
  * (||r|| <= tol ||b||, residual recomputed once on first hit; call site iterative_solver.py:995-1005).
  *   K_local: explicit local rows [n_local, n] (ld_k) or NULL for the matrix-free operator
- *   T: preconditioner factor [k, n_local] or NULL (identity); precon_sign as in mlffpc_precon_apply
+ *   T: preconditioner factor [k, n_local] or NULL (identity); precon_sign, Mk (may be NULL) as in
+ *      mlffpc_precon_apply
  *   b, x: local rows (x in: initial guess, out: solution)
  *   out_host[8] (host doubles): iterations, final ||r||, info (0 converged), ||b||,
  *       summed operator ms, operator calls, summed preconditioner ms (CUDA events), reserved
@@ -180,7 +191,7 @@ int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld,
  * Workspace: mlffpc_pcg_workspace_bytes. */
 int mlffpc_pcg_workspace_bytes(mlffpc_ctx* ctx, int64_t k, int matrix_free, int64_t* bytes);
 int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam, const double* T,
-               int64_t k, int64_t ld_t, double precon_sign, const double* b, double* x, double tol,
+               int64_t k, int64_t ld_t, double precon_sign, const double* Mk, const double* b, double* x, double tol,
                int64_t maxiter, double* out_host, double* resid_hist_host, void* workspace,
                int64_t workspace_bytes, void* stream);
 

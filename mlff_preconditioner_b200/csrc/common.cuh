@@ -91,6 +91,9 @@ struct mlffpc_ctx {
     // partition used by the symmetric tile operator; follows the communicator unless overridden by the
     // options "layout_rank"/"layout_world" (rank emulation on one GPU, tests only)
     int lay_rank = 0, lay_world = 1;
+    int64_t syrk_chunk = 0;        // option "syrk_chunk": > 0 = Gram matrices by column chunks with Kahan-summed partials
+    int tgemv_msplit = 0;          // option "tgemv_msplit": force the row split of T^T u (1, 4, 8; 0 = auto)
+    int dot_split = 1;             // option "dot_split": CG dot products as the sum of this many chunk sums (diagnostics)
     int precon_accuracy = 0;       // option "precon_accuracy": 1 = Kahan-compensated T r and T^T u (diagnostics)
     bool pchol_lookahead = true;   // option "pchol_lookahead": candidate-panel (blocked) pivoted Cholesky
     long long last_pchol_refills = 0;  // panel rebuilds of the last mlffpc_pchol_build (diagnostics)
@@ -141,7 +144,8 @@ int launch_gemv_rows(const double* K, int64_t n_rows, int64_t n_cols, int64_t ld
                      bool compensated = false);
 int launch_tgemv_cols(const double* T, int64_t k, int64_t n_cols, int64_t ld, const double* w,
                       double* out, int post, const double* r, double sign_over_lam, int num_sms,
-                      cudaStream_t s, bool compensated = false);
+                      cudaStream_t s, bool compensated = false, int force_msplit = 0, const double* w2 = nullptr,
+                      double sign = 1.0);
 // symmetric operator (symop.cu, symtma.cu)
 int64_t symv_ws_bytes(int64_t n);
 int launch_symv(mlffpc_ctx* ctx, const double* K, int64_t n, int64_t ld, const double* x, double* y, double alpha,
@@ -169,7 +173,7 @@ int matvec_free(mlffpc_ctx* ctx, const double* v, double* y_local, double alpha,
                 void* workspace, cudaStream_t s);
 // preconditioner apply (precon.cu)
 int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
-                 const double* r, double* z, double* u, cudaStream_t s);
+                 const double* r, double* z, double* u, cudaStream_t s, const double* Mk = nullptr);
 
 // internal dense building blocks (dense.cu), all on `s`
 int dgemm(bool transB, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,

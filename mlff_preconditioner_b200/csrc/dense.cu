@@ -198,6 +198,20 @@ __global__ void symmetrize_shift_kernel(double* W, int64_t m, int64_t ldw, doubl
     else if (c == r) W[r * ldw + c] += shift;
 }
 
+// W (+ running compensation C) += P, entrywise Kahan summation over the lower triangle (first = 1: W = P, C = 0)
+__global__ void kahan_accumulate_kernel(double* __restrict__ W, double* __restrict__ C, const double* __restrict__ P,
+                                        int64_t m, int64_t ldw, int first) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = blockIdx.y;
+    if (c >= m || c > r) return;
+    const int64_t iw = r * ldw + c, ip = r * m + c;
+    if (first) { W[iw] = P[ip]; C[ip] = 0.0; return; }
+    const double y = P[ip] - C[ip];
+    const double t = W[iw] + y;
+    C[ip] = (t - W[iw]) - y;
+    W[iw] = t;
+}
+
 // ---- blocked Cholesky (lower, in place) --------------------------------------------------------
 constexpr int POTRF_NB = 64;
 
@@ -313,7 +327,27 @@ int mlffpc_syrk_rows(mlffpc_ctx* ctx, const double* X, int64_t m, int64_t n_cols
     cudaStream_t s = (cudaStream_t)stream;
     ProfWindow pw = prof_window("syrk");
     pw.step(pw.first);
-    const int st_gemm = dgemm(true, m, m, n_cols, 1.0, X, ldx, X, ldx, 0.0, W, ldw, true, s);
+    int st_gemm = MLFFPC_OK;
+    const int64_t chunk = ctx->syrk_chunk;
+    if (chunk > 0 && n_cols > chunk) {
+        // The Gram of 1e5-long rows loses ~sqrt(n) eps relative accuracy in a single running sum; against
+        // lam = 1e-10 that is a visible perturbation of the Woodbury inverse ("Woodbury accuracy").
+        // Column chunks are multiplied separately (DMMA) and their partial Grams added with Kahan compensation.
+        double* tmp = nullptr;
+        MLFFPC_CUDA(cudaMallocAsync((void**)&tmp, (size_t)(2 * m * m) * sizeof(double), s));
+        double* comp = tmp + m * m;
+        const dim3 grid((unsigned)((m + 255) / 256), (unsigned)m);
+        for (int64_t c0 = 0; c0 < n_cols && st_gemm == MLFFPC_OK; c0 += chunk) {
+            const int64_t w = (n_cols - c0 < chunk) ? (n_cols - c0) : chunk;
+            st_gemm = dgemm(true, m, m, w, 1.0, X + c0, ldx, X + c0, ldx, 0.0, tmp, m, true, s);
+            if (st_gemm != MLFFPC_OK) break;
+            kahan_accumulate_kernel<<<grid, 256, 0, s>>>(W, comp, tmp, m, ldw, c0 == 0 ? 1 : 0);
+            ++g_launches;
+        }
+        cudaFreeAsync(tmp, s);
+    } else {
+        st_gemm = dgemm(true, m, m, n_cols, 1.0, X, ldx, X, ldx, 0.0, W, ldw, true, s);
+    }
     pw.end();
     MLFFPC_TRY(st_gemm);
     if (ctx->comm.world > 1) {

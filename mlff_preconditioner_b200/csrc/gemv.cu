@@ -115,16 +115,19 @@ gemv_rows_kernel(const double* __restrict__ K, int64_t n_rows, int64_t n_cols, i
 // POST: 0 = plain store; 1 = precon apply: out = sign*(r - acc)/lam.
 constexpr int TGEMV_THREADS = 256;
 
-template <int MSPLIT, bool COMP>
+// MODE 0: plain; 1: Kahan-compensated (diagnostics); 2: two weight vectors in one pass over T,
+//   out = sign * ((r - sum T w) / lam + sum T w2)      (orthonormal-basis form of the low-rank inverse)
+template <int MSPLIT, int MODE>
 __global__ void __launch_bounds__(TGEMV_THREADS)
 tgemv_cols_kernel(const double* __restrict__ T, int64_t k, int64_t n_cols, int64_t ld,
-                  const double* __restrict__ w, double* __restrict__ out, int post,
-                  const double* __restrict__ r, double sign_over_lam) {
+                  const double* __restrict__ w, const double* __restrict__ w2, double* __restrict__ out, int post,
+                  const double* __restrict__ r, double sign_over_lam, double sign) {
     constexpr int COLS = TGEMV_THREADS / MSPLIT;
     __shared__ double red[MSPLIT][COLS];
+    __shared__ double red2[MODE == 2 ? MSPLIT : 1][COLS];
     const int tc = threadIdx.x % COLS, ts = threadIdx.x / COLS;
     const int64_t c = (int64_t)blockIdx.x * COLS + tc;
-    double acc = 0.0, cmp = 0.0;
+    double acc = 0.0, cmp = 0.0, acc2 = 0.0;
     if (c < n_cols) {
         const double* Tp = T + c;
         int64_t m = ts;
@@ -135,24 +138,32 @@ tgemv_cols_kernel(const double* __restrict__ T, int64_t k, int64_t n_cols, int64
             for (int u = 0; u < 8; ++u) t[u] = __ldcs(Tp + (m + u * MSPLIT) * ld);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                if (COMP) kahan_fma(t[u], __ldg(w + m + u * MSPLIT), acc, cmp);
+                if (MODE == 1) kahan_fma(t[u], __ldg(w + m + u * MSPLIT), acc, cmp);
                 else acc = fma(t[u], __ldg(w + m + u * MSPLIT), acc);
+                if (MODE == 2) acc2 = fma(t[u], __ldg(w2 + m + u * MSPLIT), acc2);
             }
         }
         for (; m < k; m += MSPLIT) {
-            if (COMP) kahan_fma(__ldcs(Tp + m * ld), __ldg(w + m), acc, cmp);
-            else acc = fma(__ldcs(Tp + m * ld), __ldg(w + m), acc);
+            const double t = __ldcs(Tp + m * ld);
+            if (MODE == 1) kahan_fma(t, __ldg(w + m), acc, cmp);
+            else acc = fma(t, __ldg(w + m), acc);
+            if (MODE == 2) acc2 = fma(t, __ldg(w2 + m), acc2);
         }
     }
     if (MSPLIT > 1) {
         red[ts][tc] = acc;
+        if (MODE == 2) red2[ts][tc] = acc2;
         __syncthreads();
         if (ts != 0) return;
 #pragma unroll
-        for (int s = 1; s < MSPLIT; ++s) acc += red[s][tc];
+        for (int s = 1; s < MSPLIT; ++s) {
+            acc += red[s][tc];
+            if (MODE == 2) acc2 += red2[s][tc];
+        }
     }
     if (c < n_cols) {
-        if (post == 1) acc = sign_over_lam * (r[c] - acc);
+        if (MODE == 2) acc = fma(sign_over_lam, r[c] - acc, sign * acc2);
+        else if (post == 1) acc = sign_over_lam * (r[c] - acc);
         out[c] = acc;
     }
 }
@@ -182,20 +193,25 @@ int launch_gemv_rows(const double* K, int64_t n_rows, int64_t n_cols, int64_t ld
 
 int launch_tgemv_cols(const double* T, int64_t k, int64_t n_cols, int64_t ld, const double* w,
                       double* out, int post, const double* r, double sign_over_lam, int num_sms,
-                      cudaStream_t s, bool compensated) {
+                      cudaStream_t s, bool compensated, int force_msplit, const double* w2, double sign) {
     if (n_cols <= 0) return MLFFPC_OK;
     // enough threads to keep HBM busy: aim for >= 2 full waves of 256-thread CTAs
     const int64_t want = (int64_t)num_sms * 2048;
-#define MLFFPC_TGEMV(MS, CP, COLS)                                                                                  \
-    tgemv_cols_kernel<MS, CP><<<(unsigned)((n_cols + (COLS)-1) / (COLS)), TGEMV_THREADS, 0, s>>>(T, k, n_cols, ld, w, out, \
-                                                                                                 post, r, sign_over_lam)
-    if (n_cols >= want || k < 64) {
-        if (compensated) MLFFPC_TGEMV(1, true, 256); else MLFFPC_TGEMV(1, false, 256);
-    } else if (n_cols * 4 >= want || k < 256) {
-        if (compensated) MLFFPC_TGEMV(4, true, 64); else MLFFPC_TGEMV(4, false, 64);
-    } else {
-        if (compensated) MLFFPC_TGEMV(8, true, 32); else MLFFPC_TGEMV(8, false, 32);
-    }
+    const int ms = force_msplit ? force_msplit : ((n_cols >= want || k < 64) ? 1 : (n_cols * 4 >= want || k < 256) ? 4 : 8);
+    const int mode = w2 ? 2 : (compensated ? 1 : 0);
+#define MLFFPC_TGEMV(MS, MD, COLS)                                                                                  \
+    tgemv_cols_kernel<MS, MD><<<(unsigned)((n_cols + (COLS)-1) / (COLS)), TGEMV_THREADS, 0, s>>>(                   \
+        T, k, n_cols, ld, w, w2, out, post, r, sign_over_lam, sign)
+#define MLFFPC_TGEMV_MODES(MS, COLS)                                 \
+    do {                                                             \
+        if (mode == 2) MLFFPC_TGEMV(MS, 2, COLS);                    \
+        else if (mode == 1) MLFFPC_TGEMV(MS, 1, COLS);               \
+        else MLFFPC_TGEMV(MS, 0, COLS);                              \
+    } while (0)
+    if (ms == 1) MLFFPC_TGEMV_MODES(1, 256);
+    else if (ms == 4) MLFFPC_TGEMV_MODES(4, 64);
+    else MLFFPC_TGEMV_MODES(8, 32);
+#undef MLFFPC_TGEMV_MODES
 #undef MLFFPC_TGEMV
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;

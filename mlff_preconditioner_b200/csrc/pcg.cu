@@ -81,6 +81,14 @@ __global__ void residual_kernel(const double* __restrict__ b, const double* __re
     grid_reduce_store(v, partials, counter, rr);
 }
 
+__global__ void sum_slots_kernel(double* out, const double* parts, int count) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < count; ++i) t += parts[i];
+        *out = t;
+    }
+}
+
 static inline unsigned vec_grid(int64_t n) {
     int64_t g = (n + VEC_THREADS - 1) / VEC_THREADS;
     if (g > VEC_MAX_BLOCKS) g = VEC_MAX_BLOCKS;
@@ -154,7 +162,7 @@ int mlffpc_pcg_workspace_bytes(mlffpc_ctx* ctx, int64_t k, int matrix_free, int6
 }
 
 int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam, const double* T,
-               int64_t k, int64_t ld_t, double precon_sign, const double* b, double* x, double tol,
+               int64_t k, int64_t ld_t, double precon_sign, const double* Mk, const double* b, double* x, double tol,
                int64_t maxiter, double* out_host, double* resid_hist_host, void* workspace,
                int64_t workspace_bytes, void* stream) {
     MLFFPC_REQUIRE(ctx && ctx->M > 0, "pcg: geometry not set");
@@ -187,6 +195,24 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     unsigned* counter = (unsigned*)(sc + S_COUNTER);
     const unsigned g = vec_grid(nl);
 
+    // dot(a, b) -> *out; with dot_split > 1 the sum is formed chunk by chunk like a multi-rank run would (diagnostics)
+    const int dsplit = ctx->dot_split;
+    auto dot_to = [&](const double* a, const double* bvec, double* out) -> int {
+        if (dsplit <= 1) {
+            dot_kernel<<<g, VEC_THREADS, 0, s>>>(a, bvec, nl, ctx->partials, counter, out);
+            MLFFPC_LAUNCH_CHECK();
+            return MLFFPC_OK;
+        }
+        const int64_t chunk = (nl + dsplit - 1) / dsplit;
+        for (int c = 0; c < dsplit; ++c) {
+            const int64_t o = c * chunk, len = (o + chunk <= nl) ? chunk : (nl - o > 0 ? nl - o : 0);
+            dot_kernel<<<vec_grid(len), VEC_THREADS, 0, s>>>(a + o, bvec + o, len, ctx->partials, counter, sc + 16 + c);
+            MLFFPC_LAUNCH_CHECK();
+        }
+        sum_slots_kernel<<<1, 32, 0, s>>>(out, sc + 16, dsplit);
+        MLFFPC_LAUNCH_CHECK();
+        return MLFFPC_OK;
+    };
     auto host_scalar = [&](int slot, double* out) -> int {
         MLFFPC_CUDA(cudaMemcpyAsync(ctx->h_scal, sc + slot, 8, cudaMemcpyDeviceToHost, s));
         MLFFPC_CUDA(cudaStreamSynchronize(s));
@@ -247,13 +273,12 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
         // z = P r
         cudaEventRecord(ev[0], s);
         if (T) {
-            MLFFPC_TRY(precon_apply(ctx, T, k, ld_t, lam, precon_sign, r, z, u, s));
+            MLFFPC_TRY(precon_apply(ctx, T, k, ld_t, lam, precon_sign, r, z, u, s, Mk));
         } else {
             MLFFPC_CUDA(cudaMemcpyAsync(z, r, nl * 8, cudaMemcpyDeviceToDevice, s));
         }
         cudaEventRecord(ev[1], s);
-        dot_kernel<<<g, VEC_THREADS, 0, s>>>(r, z, nl, ctx->partials, counter, rho);
-        MLFFPC_LAUNCH_CHECK();
+        MLFFPC_TRY(dot_to(r, z, rho));
         MLFFPC_TRY(comm_allreduce_sum(ctx->comm, rho, 1, s));
         update_p_kernel<<<g, VEC_THREADS, 0, s>>>(z, p, nl, rho, rho_prev, it == 1 ? 1 : 0);
         MLFFPC_LAUNCH_CHECK();
@@ -261,8 +286,7 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
         cudaEventRecord(ev[2], s);
         MLFFPC_TRY(A.apply(p_full, q, s));
         cudaEventRecord(ev[3], s);
-        dot_kernel<<<g, VEC_THREADS, 0, s>>>(p, q, nl, ctx->partials, counter, sc + S_PQ);
-        MLFFPC_LAUNCH_CHECK();
+        MLFFPC_TRY(dot_to(p, q, sc + S_PQ));
         MLFFPC_TRY(comm_allreduce_sum(ctx->comm, sc + S_PQ, 1, s));
         update_xr_kernel<<<g, VEC_THREADS, 0, s>>>(x, r, p, q, nl, rho, sc + S_PQ, ctx->partials, counter, sc + S_RR);
         MLFFPC_LAUNCH_CHECK();

@@ -12,9 +12,11 @@ __global__ void add_inplace_kernel(double* __restrict__ a, const double* __restr
     if (t < n) a[t] += b[t];
 }
 
-// u: device scratch of 2 k + 4 doubles
+// u: device scratch of 2 k + 4 doubles.  Mk == NULL: Woodbury form z = sign (r - T^T T r) / lam.
+// Mk != NULL: T holds an orthonormal basis Q^T of range(L) and Mk = (Q^T L L^T Q + lam I)^{-1}:
+//   z = sign ( (r - Q (Q^T r)) / lam + Q Mk (Q^T r) ).
 int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
-                 const double* r, double* z, double* u, cudaStream_t s) {
+                 const double* r, double* z, double* u, cudaStream_t s, const double* Mk) {
     const int64_t nl = ctx->n_local();
     // u = T r  (local part), summed over ranks
     const bool comp = ctx->precon_accuracy == 1;
@@ -30,9 +32,39 @@ int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double
         MLFFPC_TRY(launch_gemv_rows(T, k, nl, ld, r, u, 1.0, 0.0, 0, s, comp));
     }
     MLFFPC_TRY(comm_allreduce_sum(ctx->comm, u, (size_t)k, s));
+    if (Mk) {
+        double* u2 = u + k + 2;
+        MLFFPC_TRY(launch_gemv_rows(Mk, k, k, k, u, u2, 1.0, 0.0, 0, s, false));  // replicated k x k product
+        return launch_tgemv_cols(T, k, nl, ld, u, z, 1, r, sign / lam, ctx->num_sms, s, false, ctx->tgemv_msplit, u2, sign);
+    }
     // z = sign (r - T^T u) / lam
-    MLFFPC_TRY(launch_tgemv_cols(T, k, nl, ld, u, z, 1, r, sign / lam, ctx->num_sms, s, comp));
+    MLFFPC_TRY(launch_tgemv_cols(T, k, nl, ld, u, z, 1, r, sign / lam, ctx->num_sms, s, comp, ctx->tgemv_msplit));
     return MLFFPC_OK;
+}
+
+__global__ void transpose_kernel(const double* __restrict__ A, double* __restrict__ At, int64_t m) {
+    __shared__ double tile[32][33];
+    const int64_t bx = (int64_t)blockIdx.x * 32, by = (int64_t)blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+        if (by + i < m && bx + threadIdx.x < m) tile[i][threadIdx.x] = A[(by + i) * m + bx + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+        if (bx + i < m && by + threadIdx.x < m) At[(bx + i) * m + by + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+__global__ void set_identity_kernel(double* __restrict__ A, int64_t m) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = blockIdx.y;
+    if (c < m) A[r * m + c] = (c == r) ? 1.0 : 0.0;
+}
+
+// lower -> full symmetric, diagonal += shift (packed k x k)
+__global__ void mirror_shift_kernel(double* W, int64_t m, double shift) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = blockIdx.y;
+    if (c >= m) return;
+    if (c > r) W[r * m + c] = W[c * m + r];
+    else if (c == r) W[r * m + c] += shift;
 }
 
 __global__ void scale_copy_kernel(const double* __restrict__ r, double* __restrict__ z, int64_t n, double a) {
@@ -64,8 +96,55 @@ int mlffpc_woodbury_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, d
     return st;
 }
 
+int mlffpc_orthonormal_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, double lam, double* Mk,
+                              double* W1, double* W2, void* stream) {
+    MLFFPC_REQUIRE(ctx && ctx->M > 0, "orthonormal_factor: geometry not set");
+    MLFFPC_REQUIRE(Lt && Mk && W1 && W2 && k > 0 && ld >= ctx->n_local() && lam > 0.0, "orthonormal_factor: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t nl = ctx->n_local();
+    const dim3 g2((unsigned)((k + 255) / 256), (unsigned)k);
+    const dim3 gt((unsigned)((k + 31) / 32), (unsigned)((k + 31) / 32)), bt(32, 8);
+    auto chol = [&](double* W) -> int {
+        int info = 0;
+        MLFFPC_TRY(mlffpc_potrf_lower(ctx, W, k, k, &info, stream));
+        if (info != 0) {
+            set_error("%d-th leading minor of the array is not positive definite", info);
+            return MLFFPC_ERR_LINALG;
+        }
+        return MLFFPC_OK;
+    };
+    ProfWindow pw = prof_window("woodbury");
+    pw.step(pw.first);
+    // CholeskyQR2 of L (rows of Lt):  Lt = C1 C2 Qt with Qt Qt^T = I to working precision (cond(L) << 1e8)
+    MLFFPC_TRY(mlffpc_syrk_rows(ctx, Lt, k, nl, ld, 0.0, W1, k, stream));
+    MLFFPC_TRY(chol(W1));
+    MLFFPC_TRY(mlffpc_trsm_rows(ctx, W1, k, k, Lt, nl, ld, stream));
+    MLFFPC_TRY(mlffpc_syrk_rows(ctx, Lt, k, nl, ld, 0.0, W2, k, stream));
+    MLFFPC_TRY(chol(W2));
+    MLFFPC_TRY(mlffpc_trsm_rows(ctx, W2, k, k, Lt, nl, ld, stream));
+    // B = C1 C2 (lower triangular): L L^T = Q (B^T B) Q^T.   S = B^T B + lam I
+    MLFFPC_TRY(dgemm(false, k, k, k, 1.0, W1, k, W2, k, 0.0, Mk, k, false, s));
+    transpose_kernel<<<gt, bt, 0, s>>>(Mk, W2, k);                                   // W2 = B^T
+    MLFFPC_LAUNCH_CHECK();
+    MLFFPC_TRY(dgemm(true, k, k, k, 1.0, W2, k, W2, k, 0.0, W1, k, true, s));         // W1 = B^T B (lower tiles)
+    mirror_shift_kernel<<<g2, 256, 0, s>>>(W1, k, lam);
+    MLFFPC_LAUNCH_CHECK();
+    // Mk = S^{-1} = Y^T Y with Y = chol(S)^{-1}
+    MLFFPC_TRY(chol(W1));
+    set_identity_kernel<<<g2, 256, 0, s>>>(W2, k);
+    MLFFPC_LAUNCH_CHECK();
+    MLFFPC_TRY(mlffpc_trsm_rows(ctx, W1, k, k, W2, k, k, stream));                    // W2 = Y
+    transpose_kernel<<<gt, bt, 0, s>>>(W2, W1, k);                                   // W1 = Y^T
+    MLFFPC_LAUNCH_CHECK();
+    MLFFPC_TRY(dgemm(true, k, k, k, 1.0, W1, k, W1, k, 0.0, Mk, k, true, s));         // Mk = Y^T Y (lower tiles)
+    mirror_shift_kernel<<<g2, 256, 0, s>>>(Mk, k, 0.0);
+    MLFFPC_LAUNCH_CHECK();
+    pw.end();
+    return MLFFPC_OK;
+}
+
 int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
-                        const double* r, double* z, double* u, void* stream) {
+                        const double* r, double* z, double* u, const double* Mk, void* stream) {
     MLFFPC_REQUIRE(ctx && ctx->M > 0, "precon_apply: geometry not set");
     MLFFPC_REQUIRE(r && z && lam > 0.0, "precon_apply: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
@@ -76,7 +155,7 @@ int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld,
         return MLFFPC_OK;
     }
     MLFFPC_REQUIRE(u && ld >= ctx->n_local(), "precon_apply: bad argument");
-    return precon_apply(ctx, T, k, ld, lam, sign, r, z, u, s);
+    return precon_apply(ctx, T, k, ld, lam, sign, r, z, u, s, Mk);
 }
 
 }  // extern "C"

@@ -191,8 +191,25 @@ class Iterative(object):
             sync()
             self.timings['pchol_build'] = timeit.default_timer() - start_preconditioner
             info_cholesky = {'time_cholesky': step_s, 'L.shape': (n, k), 'index_columns': idx_t.cpu().numpy()}
-            T = eng.woodbury_factor_(Lt, lam) if k > 0 else None
-            P_op = LowRankPreconditioner(eng, T, lam, 1.0)
+            # (L L^T + lam I)^{-1}: 'woodbury' is the reference's formula (iterative_cholesky.py:141-148);
+            # 'orthonormal' (default) is the same operator evaluated without the 1/lam cancellation
+            form = task.get('precon_form', 'orthonormal')
+            if form not in ('orthonormal', 'woodbury'):
+                raise ValueError("task['precon_form'] must be 'orthonormal' or 'woodbury'")
+            Mk = None
+            if k == 0:
+                T = None
+            elif form == 'woodbury':
+                T = eng.woodbury_factor_(Lt, lam)
+            else:
+                try:
+                    T, Mk = eng.orthonormal_factor_(Lt, lam)
+                except np.linalg.LinAlgError:
+                    # L^T L is numerically singular (pivots far below eps * max): only the shifted Gram of the
+                    # reference's formula is positive definite.  Lt is untouched when the first Cholesky fails.
+                    T, Mk, form = eng.woodbury_factor_(Lt, lam), None, 'woodbury'
+            self.timings['precon_form'] = form
+            P_op = LowRankPreconditioner(eng, T, lam, 1.0, Mk=Mk)
             inducing_pts_idxs = np.arange(int(break_percentage * n))  # :792
         else:
             raise NotImplementedError(f'str_preconditioner = {str_preconditioner}')
@@ -218,7 +235,8 @@ class Iterative(object):
         tic_start = timeit.default_timer()
         res = eng.pcg(
             y_t[eng.row0:eng.row0 + eng.n_local].contiguous(), lam, task['solver_tol'], maxiter,
-            K_local=self.K_local, T=P_op.T, precon_sign=P_op.sign, x0=x0, want_hist=bool(task.get('_want_hist')))
+            K_local=self.K_local, T=P_op.T, precon_sign=P_op.sign, x0=x0, want_hist=bool(task.get('_want_hist')),
+            Mk=P_op.Mk)
         x, iters, resid, info, bnrm2 = res[:5]
         if task.get('_want_hist'):
             self.timings['resid_hist_rel'] = res[5] / bnrm2

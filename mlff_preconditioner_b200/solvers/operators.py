@@ -49,11 +49,13 @@ class KernelOperator(_DeviceOperator):
 class LowRankPreconditioner(_DeviceOperator):
     """``a -> sign * (a - T^T (T a)) / lam`` with T[k, n_local] on the device.
     sign = +1: pivoted-Cholesky Woodbury inverse (iterative_cholesky.py:145-148);
-    sign = -1: Nystroem operators (iterative_solver.py:315-318, :376-379)."""
+    sign = -1: Nystroem operators (iterative_solver.py:315-318, :376-379).
+    With ``Mk`` the same inverse is held in an orthonormal basis (``Engine.orthonormal_factor_``):
+    ``a -> sign * ((a - T^T T a)/lam + T^T Mk T a)``."""
 
-    def __init__(self, engine, T, lam, sign):
+    def __init__(self, engine, T, lam, sign, Mk=None):
         super().__init__(engine)
-        self.T, self.lam, self.sign = T, float(lam), float(sign)
+        self.T, self.lam, self.sign, self.Mk = T, float(lam), float(sign), Mk
 
     def device_apply(self, a):
-        return self.engine.precon_apply(self.T, self.lam, self.sign, a)
+        return self.engine.precon_apply(self.T, self.lam, self.sign, a, Mk=self.Mk)

@@ -85,6 +85,19 @@ def test_partial_cholesky_properties(full):
     full['Lt'] = Lt
 
 
+def test_lookahead_and_plain_pivoted_cholesky_agree(full):
+    """The blocked (candidate-panel) build and the plain left-looking build choose the same pivots and give the
+    same factor up to summation order."""
+    torch, eng = full['torch'], full['eng']
+    diag0 = eng.kernel_diag()
+    eng.set_option('pchol_lookahead', 0)
+    Lt0, idx0, _, _ = eng.pchol_build(K_RANK, diag=diag0, want_times=False)
+    eng.set_option('pchol_lookahead', 1)
+    Lt1, idx1, _, _ = eng.pchol_build(K_RANK, diag=diag0, want_times=False)
+    assert torch.equal(idx0, idx1)
+    assert float((Lt0 - Lt1).abs().max()) <= 1e-11 * float(Lt0.abs().max())
+
+
 def test_woodbury_inverse_property(full):
     torch, eng = full['torch'], full['eng']
     Lt = full.get('Lt')

@@ -346,3 +346,46 @@ def test_symmetric_tile_operator_emulated_ranks(torch_cuda, golden, case):
     out = eng.symop_apply(Ksym, v, alpha=1.0, shift=-lam).cpu().numpy()
     assert relerr(out, g['K_op_v']) < TOL
     assert np.array_equal(out, eng.symop_apply(Ksym, v, alpha=1.0, shift=-lam).cpu().numpy())  # deterministic
+
+
+def test_orthonormal_form_of_the_low_rank_inverse(torch_cuda, golden):
+    """(L L^T + lam I)^{-1} a three ways: dense solve (torch, fp64), the reference's Woodbury formula
+    (iterative_cholesky.py:141-148) and the orthonormal-basis form (CholeskyQR2 + k x k inverse).  At lam = 1e-3
+    all agree to 1e-9; at the solver's lam = 1e-10 the orthonormal form keeps the range part accurate
+    (checked against the dense solve on vectors in range(L), where Woodbury's subtraction cancels)."""
+    torch = torch_cuda
+    from mlff_preconditioner_b200 import synthetic
+    from mlff_preconditioner_b200.desc import Desc, tril_perms_lin_from_perms
+    from mlff_preconditioner_b200.engine import Engine
+
+    M = 80
+    ds = synthetic.make_dataset('ethanol', M, seed=3)
+    desc = Desc(9)
+    perms = np.arange(9)[None]
+    R_desc, R_d_desc = desc.from_R(ds['R'].reshape(M, -1))
+    eng = Engine(R_desc, R_d_desc, tril_perms_lin_from_perms(perms, desc), 10, perms=perms)
+    k = 216
+    Lt, _, _, _ = eng.pchol_build(k)
+    L = Lt.t().contiguous()
+    gen = torch.Generator(device=eng.device).manual_seed(7)
+    a = torch.randn(eng.n, dtype=torch.float64, device=eng.device, generator=gen)
+    eye = torch.eye(eng.n, dtype=torch.float64, device=eng.device)
+    for lam in (1e-3,):
+        ref = torch.linalg.solve(L @ L.t() + lam * eye, a)
+        T = eng.woodbury_factor_(Lt.clone(), lam)
+        Qt, Mk = eng.orthonormal_factor_(Lt.clone(), lam)
+        assert float((Qt @ Qt.t() - torch.eye(k, dtype=torch.float64, device=eng.device)).abs().max()) < 1e-13
+        out_w = eng.precon_apply(T, lam, 1.0, a)
+        out_o = eng.precon_apply(Qt, lam, 1.0, a, Mk=Mk)
+        assert relerr(out_w.cpu().numpy(), ref.cpu().numpy()) < 1e-9
+        assert relerr(out_o.cpu().numpy(), ref.cpu().numpy()) < 1e-9
+        assert relerr(eng.precon_apply(Qt, lam, -1.0, a, Mk=Mk).cpu().numpy(), -ref.cpu().numpy()) < 1e-9
+    # lam = 1e-10, a in range(L): the exact answer is L (L^T L + lam I)^{-1} c for a = L c
+    lam = 1e-10
+    c = torch.randn(k, dtype=torch.float64, device=eng.device, generator=gen)
+    a = L @ c
+    G = Lt @ L
+    ref = L @ torch.linalg.solve(G + lam * torch.eye(k, dtype=torch.float64, device=eng.device), c)
+    Qt, Mk = eng.orthonormal_factor_(Lt.clone(), lam)
+    out_o = eng.precon_apply(Qt, lam, 1.0, a, Mk=Mk)
+    assert relerr(out_o.cpu().numpy(), ref.cpu().numpy()) < 1e-5
