@@ -198,8 +198,9 @@ def run_reference_arm(args):
         return
     inp = make_inputs(args.workload, args.M, args.tol, args.k)
     consts = load_constants().get(args.workload, {})
-    cg_iters = int(consts.get('cg_iters', 1000))
-    src = 'bench_constants.json' if 'cg_iters' in consts else 'assumed (no GPU run recorded yet)'
+    cg_iters = int(consts.get('cg_iters_reference_form', 1000))
+    src = ('bench_constants.json (measured on B200 with the reference\'s Woodbury formula, precon_form=woodbury)'
+           if 'cg_iters_reference_form' in consts else 'assumed (no GPU run recorded yet)')
     for _ in range(args.warmup):
         cpu_reference_sample(inp, cg_iters, light=True)
     vals, detail = [], None
@@ -226,11 +227,15 @@ def run_reference_arm(args):
 
 
 def workload_config(inp, args, world):
-    return {'workload': '%s: synthetic %s-size N=%d M=%d n=%d, assembled fp64 kernel (%.1f GB) row-block sharded over %d GPU(s), '
-                        "'cholesky' preconditioner k=%d, tol=%g, sig=10, lam=1e-10"
-                        % (args.workload, inp['kind'], inp['N'], inp['M'], inp['n'], 8.0 * inp['n'] ** 2 / 1e9, world,
-                           inp['k'], inp['tol']),
-            'kernel_mode': args.mode, 'n': inp['n'], 'k': inp['k'], 'tol': inp['tol'],
+    storage = {'assembled': 'assembled fp64 kernel (%.1f GB) row-block sharded' % (8.0 * inp['n'] ** 2 / 1e9),
+               'assembled_sym': 'assembled fp64 kernel in symmetric tile storage (%.1f GB, every entry of the lower '
+                                'block triangle stored and read once) sharded' % (4.0 * inp['n'] ** 2 / 1e9),
+               'matrix_free': 'matrix-free kernel operator sharded'}[args.mode]
+    return {'workload': "%s: synthetic %s-size N=%d M=%d n=%d, %s over %d GPU(s), 'cholesky' (pivoted partial Cholesky) "
+                        'preconditioner k=%d, tol=%g, sig=10, lam=1e-10'
+                        % (args.workload, inp['kind'], inp['N'], inp['M'], inp['n'], storage, world, inp['k'], inp['tol']),
+            'kernel_mode': args.mode, 'precon_form': args.precon_form or 'orthonormal', 'n': inp['n'], 'k': inp['k'],
+            'tol': inp['tol'],
             'l2_policy': 'inputs larger than L2: K (>= 11.7 GB per GPU) is re-assembled and streamed every step'}
 
 
@@ -414,19 +419,15 @@ def run_ours(args):
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        total, detail = cpu_reference_sample(inp, iters)
+        ref_iters = int(load_constants().get(args.workload, {}).get('cg_iters_reference_form', iters))
+        total, detail = cpu_reference_sample(inp, ref_iters)
         line['cpu_baseline'] = {
             'value': total, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'port', 'extrapolated': True,
             'sample': '2 full-n torch-CPU kernel matvecs, 2 Schur-update steps at m=k/2, Woodbury factor at k\'=512 '
                       '(scaled (k/k\')^2), 3 applies at k\' (scaled k/k\'); solve = k(t_mv+t_sch)+t_fac+iters(t_mv+t_app) '
-                      'with the GPU run\'s k and iteration count',
+                      'with the GPU run\'s k and the iteration count measured for the reference\'s Woodbury formula '
+                      '(bench_constants.json)',
             'detail': detail}
-        consts = load_constants()
-        consts.setdefault(args.workload, {})['cg_iters'] = int(iters)
-        try:
-            json.dump(consts, open(CONSTANTS_FILE, 'w'), indent=1)
-        except OSError:
-            pass
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
