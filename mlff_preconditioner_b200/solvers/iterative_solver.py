@@ -126,9 +126,9 @@ class Iterative(object):
         return KernelOperator(self.engine, lam, 1.0, self.K_local)
 
     def _choose_kernel_mode(self, task, k):
-        """'assembled' (explicit row block in HBM, GEMV per iteration) or 'matrix_free'.
-        'auto' = assembled when the row block fits next to the preconditioner, else matrix-free
-        (BASELINE.json north_star)."""
+        """'assembled_sym' (symmetric tile storage in HBM, every entry read once per iteration), 'assembled'
+        (plain row block + GEMV) or 'matrix_free'.  'auto' = the symmetric storage when it fits next to the
+        preconditioner on every rank, else matrix-free (BASELINE.json north_star)."""
         mode = task.get('kernel_mode', 'auto')
         if mode not in ('auto', 'assembled', 'assembled_sym', 'matrix_free'):
             raise ValueError("task['kernel_mode'] must be 'auto', 'assembled', 'assembled_sym' or 'matrix_free'")
@@ -136,8 +136,12 @@ class Iterative(object):
             return mode
         eng = self.engine
         free, _ = torch.cuda.mem_get_info(eng.device)
-        need = eng.n_local * eng.n * 8 + 2 * max(k, 1) * eng.n_local * 8 + (2 << 30)
-        return 'assembled' if need < free else 'matrix_free'
+        need = eng.symop_storage_elems() * 8 + (2 << 30)
+        fits = torch.tensor([1 if need < free else 0], dtype=torch.int32, device=eng.device)
+        if eng.world > 1:  # the ranks hold different tile sets: decide together
+            import torch.distributed as dist
+            dist.all_reduce(fits, op=dist.ReduceOp.MIN)
+        return 'assembled_sym' if int(fits.item()) == 1 else 'matrix_free'
 
     # ------------------------------------------------------------------ device-resident solve
     def solve_device(self, task, eng, y_t, break_percentage, str_preconditioner, n_inducing_pts, x0=None):
