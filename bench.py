@@ -241,6 +241,11 @@ def workload_config(inp, args, world):
 
 # ----------------------------------------------------------------------------- GPU arm
 def run_ours(args):
+    # rank 0 prints exactly ONE line on stdout: anything native libraries write to fd 1 (NCCL banners) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -249,8 +254,8 @@ def run_ours(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'  # the version banner goes to stdout; rank 0 prints exactly one JSON line
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+            os.environ.pop('NCCL_DEBUG')   # both levels print a version banner on stdout
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     import __graft_entry__ as g
 
@@ -429,7 +434,8 @@ def run_ours(args):
                       '(bench_constants.json)',
             'detail': detail}
     if rank == 0:
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + '\n')
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
