@@ -91,6 +91,7 @@ struct mlffpc_ctx {
     // partition used by the symmetric tile operator; follows the communicator unless overridden by the
     // options "layout_rank"/"layout_world" (rank emulation on one GPU, tests only)
     int lay_rank = 0, lay_world = 1;
+    bool assemble_legacy = false;  // option "assemble_legacy": one CTA per 3N x 3N block (the first-generation kernel)
     int64_t syrk_chunk = 0;        // option "syrk_chunk": > 0 = Gram matrices by column chunks with Kahan-summed partials
     int tgemv_msplit = 0;          // option "tgemv_msplit": force the row split of T^T u (1, 4, 8; 0 = auto)
     int dot_split = 1;             // option "dot_split": CG dot products as the sum of this many chunk sums (diagnostics)
@@ -176,8 +177,9 @@ int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double
                  const double* r, double* z, double* u, cudaStream_t s, const double* Mk = nullptr);
 
 // internal dense building blocks (dense.cu), all on `s`
+// nsplit > 1: split-K, slice z writes its partial product to C + z * c_zstride (beta applies to every slice)
 int dgemm(bool transB, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only,
-          cudaStream_t s);
+          cudaStream_t s, int nsplit = 1, int64_t c_zstride = 0);
 
 }  // namespace mlffpc

@@ -50,7 +50,17 @@ template <int BM, int BN, int WARPS_M, int WARPS_N, bool TRANSB, bool VEC2>
 __global__ void __launch_bounds__(GEMM_THREADS)
 dgemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __restrict__ A, int64_t lda,
              const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C, int64_t ldc,
-             int lower_only) {
+             int lower_only, int64_t k_chunk, int64_t c_zstride) {
+    // split-K: slice blockIdx.z multiplies columns [z k_chunk, (z+1) k_chunk) of A with the matching part of B
+    // and writes its own partial product C + z c_zstride (the caller adds the partials in a fixed order)
+    if (gridDim.z > 1) {
+        const int64_t kb = (int64_t)blockIdx.z * k_chunk;
+        A += kb;
+        B += TRANSB ? kb : kb * ldb;
+        C += (int64_t)blockIdx.z * c_zstride;
+        k = (k - kb < k_chunk) ? (k - kb) : k_chunk;
+        if (k < 0) k = 0;
+    }
     using SM = GemmSmem<BM, BN, TRANSB>;
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;  // warp tile
     constexpr int TM = WM / 8, TN = WN / 8;              // 8x8 mma tiles per warp
@@ -162,28 +172,33 @@ dgemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __rest
 template <int BM, int BN, int WARPS_M, int WARPS_N, bool TRANSB, bool VEC2>
 static int launch_dgemm(int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                         const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
-                        bool lower_only, cudaStream_t s) {
+                        bool lower_only, cudaStream_t s, int nsplit = 1, int64_t c_zstride = 0) {
     using SM = GemmSmem<BM, BN, TRANSB>;
     auto kern = dgemm_kernel<BM, BN, WARPS_M, WARPS_N, TRANSB, VEC2>;
     MLFFPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES));
-    dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
+    dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), (unsigned)nsplit);
     MLFFPC_REQUIRE(grid.y <= 65535, "dgemm: m = %lld too large for this launch shape", (long long)m);
-    kern<<<grid, GEMM_THREADS, SM::BYTES, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0);
+    // chunks are multiples of the k tile and even, so 16-byte staging stays aligned in every slice
+    int64_t k_chunk = (k + nsplit - 1) / nsplit;
+    k_chunk = (k_chunk + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+    kern<<<grid, GEMM_THREADS, SM::BYTES, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0, k_chunk,
+                                               c_zstride);
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;
 }
 
 int dgemm(bool transB, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only,
-          cudaStream_t s) {
+          cudaStream_t s, int nsplit, int64_t c_zstride) {
     if (m <= 0 || n <= 0) return MLFFPC_OK;
+    if (nsplit < 1) nsplit = 1;
     const bool vec2 = (lda % 2 == 0) && (ldb % 2 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
     const bool narrow = (n <= 64);
     const bool flat = (m <= 64) && !narrow;  // few rows, many columns (the look-ahead panel update, TRSM tails)
 #define MLFFPC_GEMM_DISPATCH(TB, V2)                                                                      \
-    (narrow ? launch_dgemm<128, 64, 4, 2, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s) \
-     : flat ? launch_dgemm<64, 128, 2, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s) \
-            : launch_dgemm<128, 128, 2, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s))
+    (narrow ? launch_dgemm<128, 64, 4, 2, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride) \
+     : flat ? launch_dgemm<64, 128, 2, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride) \
+            : launch_dgemm<128, 128, 2, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride))
     if (transB) return vec2 ? MLFFPC_GEMM_DISPATCH(true, true) : MLFFPC_GEMM_DISPATCH(true, false);
     return vec2 ? MLFFPC_GEMM_DISPATCH(false, true) : MLFFPC_GEMM_DISPATCH(false, false);
 #undef MLFFPC_GEMM_DISPATCH

@@ -217,6 +217,143 @@ __global__ void assemble_block_kernel(GeoView g, int64_t pt0, int64_t j_pt0, int
     }
 }
 
+
+// ---- explicit rows: one CTA = one row point i x up to JT column points ------------------------------------
+// Phase 1 builds, for every (column point, permutation) of the CTA, the difference vector, the coefficients
+// a_p / b_p and the two projected vectors u_i = J_i^T Delta, u_j = J_j^(p)T Delta in shared memory (all
+// threads busy: JT * S * 3N outputs).  Phase 2 gives every thread one OUTPUT COLUMN (point jj, atom A2,
+// component c2) and lets it walk down the 3N rows, so a warp stores 32 consecutive doubles of one row of K --
+// full-sector coalesced writes, the HBM-write roofline of assembly.  All index arithmetic is hoisted out of the
+// row loop; the sparse Jacobian product J_i^T J_j is one multiply per off-diagonal atom pair and an (N-1)-term
+// sum on the diagonal atoms.
+// dynamic smem (doubles): xi[D] | gi[3D] | gj[JT][3D] | dl[JT][S][D] | ui[JT][S][3N] | uj[JT][S][3N] | ab[JT][S][2]
+//                         then ints: P[S][N] | Pinv[S][N]
+constexpr int ASM_THREADS = 256;
+
+__global__ void __launch_bounds__(ASM_THREADS)
+assemble_rows_kernel(GeoView g, int64_t i_pt0, int64_t j_pt0, int64_t n_jpts, int JT, int packed,
+                     double* __restrict__ out, int64_t ld) {
+    extern __shared__ double asm_sm[];
+    const int D = g.D, di = g.dim_i, S = g.S, N = g.N;
+    double* xi = asm_sm;
+    double* gi = xi + D;
+    double* gj = gi + 3 * D;
+    double* dl = gj + (size_t)JT * 3 * D;
+    double* ui = dl + (size_t)JT * S * D;
+    double* uj = ui + (size_t)JT * S * di;
+    double* ab = uj + (size_t)JT * S * di;
+    int* P = (int*)(ab + (size_t)JT * S * 2);
+    int* Pinv = P + S * N;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t il = blockIdx.x, i = i_pt0 + il;
+    const int64_t jb = (int64_t)blockIdx.y * JT;
+    const int nj = (int)((n_jpts - jb < JT) ? (n_jpts - jb) : JT);
+    // packed diagonal tile: band b of 256 rows keeps columns [0, 256 (b + 1)); skip CTAs entirely right of that
+    if (packed && jb * di >= st_band_pitch(((il + 1) * di - 1) / ST_BAND_ROWS)) return;
+
+    for (int t = tid; t < D; t += ASM_THREADS) xi[t] = g.R_desc[i * D + t];
+    for (int t = tid; t < 3 * D; t += ASM_THREADS) gi[t] = g.R_d_desc[i * D * 3 + t];
+    for (int t = tid; t < S * N; t += ASM_THREADS) { P[t] = g.P[t]; Pinv[t] = g.Pinv[t]; }
+    for (int t = tid; t < nj * 3 * D; t += ASM_THREADS) {
+        const int jj = t / (3 * D), e = t % (3 * D);
+        gj[(size_t)jj * 3 * D + e] = g.R_d_desc[(j_pt0 + jb + jj) * D * 3 + e];
+    }
+    __syncthreads();
+    for (int t = tid; t < nj * S * D; t += ASM_THREADS) {
+        const int d = t % D, q = t / D;  // q = jj * S + p
+        const int64_t j = j_pt0 + jb + q / S;
+        dl[t] = xi[d] - g.Xp[(j * S + q % S) * (int64_t)D + d];
+    }
+    __syncthreads();
+    // a_p, b_p: one warp per (jj, p)
+    for (int q = warp; q < nj * S; q += ASM_THREADS / 32) {
+        double s2 = 0.0;
+        for (int d = lane; d < D; d += 32) { const double v = dl[(size_t)q * D + d]; s2 = fma(v, v, s2); }
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            const double rho = g.q * sqrt(s2);
+            const double e = g.pref * exp(-rho);
+            ab[2 * q] = e * g.q * g.q;
+            ab[2 * q + 1] = e * (1.0 + rho);
+        }
+    }
+    // u_i[(A,c)] = sum_{B != A} sgn(A,B) g_i[pair(A,B), c] Delta[pair(A,B)]
+    // u_j[(A2,c2)] = sum_{B != App} sgn(A2, P[B]) g_j[pair(A2, P[B]), c2] Delta[pair(App, B)],  App = Pinv[A2]
+    for (int t = tid; t < nj * S * di; t += ASM_THREADS) {
+        const int r = t % di, q = t / di, p = q % S, jj = q / S;
+        const int A = r / 3, c = r % 3;
+        const double* dq = dl + (size_t)q * D;
+        const double* gjj = gj + (size_t)jj * 3 * D;
+        const int* Pp = P + p * N;
+        const int App = Pinv[p * N + A];
+        double a1 = 0.0, a2 = 0.0;
+        for (int B = 0; B < N; ++B) {
+            if (B != A) {
+                const int d = pair_index(A, B);
+                const double t1 = gi[d * 3 + c] * dq[d];
+                a1 += (A < B) ? t1 : -t1;
+            }
+            if (B != App) {
+                const int d = pair_index(App, B);
+                const int PB = Pp[B];
+                const double t2 = gjj[pair_index(A, PB) * 3 + c] * dq[d];
+                a2 += (A < PB) ? t2 : -t2;
+            }
+        }
+        ui[t] = a1;
+        uj[t] = a2;
+    }
+    __syncthreads();
+
+    // phase 2: thread <-> output column
+    for (int col = tid; col < nj * di; col += ASM_THREADS) {
+        const int jj = col / di, r2 = col % di, A2 = r2 / 3, c2 = r2 % 3;
+        const double* gjj = gj + (size_t)jj * 3 * D;
+        const int64_t gcol = (jb + jj) * di + r2;  // column inside the tile
+        for (int A = 0; A < N; ++A) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int r = 3 * A + c;
+                double val = 0.0;
+                for (int p = 0; p < S; ++p) {
+                    const int q = jj * S + p;
+                    const int* Pp = P + p * N;
+                    const int App = Pinv[p * N + A2];
+                    double G;
+                    if (App != A) {
+                        const int PA = Pp[A];
+                        const double t = gi[pair_index(A, App) * 3 + c] * gjj[pair_index(PA, A2) * 3 + c2];
+                        G = ((A < App) == (A2 < PA)) ? t : -t;
+                    } else {
+                        G = 0.0;
+                        for (int B = 0; B < N; ++B) {
+                            if (B == A) continue;
+                            const int PB = Pp[B];
+                            const double t = gi[pair_index(A, B) * 3 + c] * gjj[pair_index(A2, PB) * 3 + c2];
+                            G += ((A < B) == (A2 < PB)) ? t : -t;
+                        }
+                    }
+                    val += ab[2 * q] * ui[(size_t)q * di + r] * uj[(size_t)q * di + r2] - ab[2 * q + 1] * G;
+                }
+                const int64_t row = il * di + r;
+                if (packed) {
+                    const int64_t b = row / ST_BAND_ROWS;
+                    if (gcol < st_band_pitch(b)) out[st_band_off(b) + (row - b * ST_BAND_ROWS) * st_band_pitch(b) + gcol] = val;
+                } else {
+                    out[row * ld + gcol] = val;
+                }
+            }
+        }
+    }
+}
+
+static size_t assemble_rows_smem(const GeoView& g, int JT) {
+    const size_t dbl = (size_t)g.D + 3 * g.D + (size_t)JT * 3 * g.D + (size_t)JT * g.S * g.D +
+                       2 * (size_t)JT * g.S * g.dim_i + (size_t)JT * g.S * 2;
+    return dbl * sizeof(double) + 2 * (size_t)g.S * g.N * sizeof(int) + 16;
+}
+
 // ---- one column restricted to the local rows: CTA per (local point i, column c) -------------
 // out[c, il*dim_i + r] = scale * K[(i, r), cols[c]]
 // dynamic smem: ab[2S] | red[40] | uj[S] | ui[S*dim_i]
@@ -392,15 +529,30 @@ int assemble_tile(mlffpc_ctx* ctx, int64_t i_pt0, int64_t i_pt1, int64_t j_pt0, 
                    "assemble_tile: bad point ranges");
     MLFFPC_REQUIRE(packed ? (i_pt0 == j_pt0 && i_pt1 == j_pt1) : (ld >= (j_pt1 - j_pt0) * ctx->dim_i),
                    "assemble_tile: ld too small / packed layout needs a square diagonal tile");
-    MLFFPC_REQUIRE(!packed || (j_pt1 - j_pt0) <= 65535, "assemble_tile: packed tiles are limited to 65535 points");
     GeoView g = make_view(ctx);
+    const int64_t ni = i_pt1 - i_pt0, nj = j_pt1 - j_pt0;
+    // row-walking kernel: JT column points per CTA so that one CTA covers ~256 output columns
+    int JT = ASM_THREADS / g.dim_i;
+    if (JT > 8) JT = 8;
+    if (JT < 1) JT = 1;
+    const size_t smem_rows = assemble_rows_smem(g, JT);
+    const int64_t gy = (nj + JT - 1) / JT;
+    if (!ctx->assemble_legacy && smem_rows <= 160 * 1024 && gy <= 65535) {
+        MLFFPC_CUDA(cudaFuncSetAttribute(assemble_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        assemble_rows_kernel<<<dim3((unsigned)ni, (unsigned)gy), ASM_THREADS, smem_rows, s>>>(g, i_pt0, j_pt0, nj, JT, packed,
+                                                                                          out, ld);
+        MLFFPC_LAUNCH_CHECK();
+        return MLFFPC_OK;
+    }
+    // fallback (very large molecules: the per-point Jacobian does not fit in shared memory): one CTA per block
+    MLFFPC_REQUIRE(!packed || nj <= 65535, "assemble_tile: packed tiles are limited to 65535 points");
     const size_t smem = (size_t)(2 * g.S + 40 + 2 * g.S * g.dim_i) * sizeof(double);
     MLFFPC_REQUIRE(smem <= 200 * 1024, "kernel_assemble: S*3N = %d too large for shared memory", g.S * g.dim_i);
     MLFFPC_CUDA(cudaFuncSetAttribute(assemble_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int block = pick_block(g.dim_i * g.dim_i);
     for (int64_t j0 = j_pt0; j0 < j_pt1; j0 += 65535) {  // grid.y limit
-        const int64_t nj = (j_pt1 - j0 < 65535) ? (j_pt1 - j0) : 65535;
-        assemble_block_kernel<false><<<dim3((unsigned)(i_pt1 - i_pt0), (unsigned)nj), block, smem, s>>>(
+        const int64_t njc = (j_pt1 - j0 < 65535) ? (j_pt1 - j0) : 65535;
+        assemble_block_kernel<false><<<dim3((unsigned)ni, (unsigned)njc), block, smem, s>>>(
             g, i_pt0, j0, packed, packed ? out : out + (j0 - j_pt0) * g.dim_i, ld);
         MLFFPC_LAUNCH_CHECK();
     }

@@ -100,15 +100,23 @@ mv_pairs_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __restr
     }
 }
 
-// CTA per local point: f = G[i,D] x_i - G[i,:D];  y = alpha J_i^T f + shift v_local
+// CTA per local point: G = sum of the split-K partials; f = G[i,D] x_i - G[i,:D];  y = alpha J_i^T f + shift v_local
 __global__ void mv_epilogue_kernel(int N, int D, int64_t pt0, const double* __restrict__ R_desc,
-                                   const double* __restrict__ R_d_desc, const double* __restrict__ G,
-                                   int64_t ldg, const double* __restrict__ v, double* __restrict__ y,
-                                   double alpha, double shift) {
+                                   const double* __restrict__ R_d_desc, double* __restrict__ G,
+                                   int64_t ldg, int nsplit, int64_t zstride, const double* __restrict__ v,
+                                   double* __restrict__ y, double alpha, double shift) {
     const int64_t il = blockIdx.x, i = pt0 + il;
     const double* xi = R_desc + i * D;
     const double* gi = R_d_desc + i * D * 3;
-    const double* Gi = G + il * ldg;
+    double* Gi = G + il * ldg;
+    if (nsplit > 1) {  // fixed-order sum of the partial products into slice 0
+        for (int d = threadIdx.x; d <= D; d += blockDim.x) {
+            double t = Gi[d];
+            for (int z = 1; z < nsplit; ++z) t += Gi[(int64_t)z * zstride + d];
+            Gi[d] = t;
+        }
+        __syncthreads();
+    }
     const double r1 = Gi[D];
     const int dim_i = 3 * N;
     for (int r = threadIdx.x; r < dim_i; r += blockDim.x) {
@@ -129,6 +137,7 @@ __global__ void mv_epilogue_kernel(int N, int D, int64_t pt0, const double* __re
 
 struct MvWs {
     int64_t ldb, off_bmat, off_cmat, off_g, total;
+    int nsplit;
 };
 static MvWs mv_layout(const mlffpc_ctx* c) {
     auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
@@ -138,7 +147,16 @@ static MvWs mv_layout(const mlffpc_ctx* c) {
     int64_t o = 0;
     w.off_bmat = o; o = up(o + 2 * MS * w.ldb * 8);
     w.off_cmat = o; o = up(o + Ml * 2 * MS * 8);
-    w.off_g = o;    o = up(o + Ml * w.ldb * 8);
+    // the contraction G = [C1|C2] [X; beta] has few output tiles and a very long k: split k until the grid
+    // covers the GPU about twice
+    const int64_t tiles = ((Ml + 127) / 128) * ((c->D + 1 + 127) / 128);
+    int64_t ns = (2 * (int64_t)c->num_sms + tiles - 1) / tiles;
+    const int64_t max_by_k = (2 * MS) / 512;  // keep >= 512 columns of k per slice
+    if (ns > max_by_k) ns = max_by_k;
+    if (ns > 32) ns = 32;
+    if (ns < 1) ns = 1;
+    w.nsplit = (int)ns;
+    w.off_g = o;    o = up(o + ns * Ml * w.ldb * 8);
     w.total = o + 256;
     return w;
 }
@@ -164,10 +182,12 @@ int matvec_free(mlffpc_ctx* ctx, const double* v, double* y_local, double alpha,
     MLFFPC_REQUIRE(grid.y <= 65535, "matvec_free: too many local points for this launch shape");
     mv_pairs_kernel<<<grid, 256, 0, s>>>(ctx->R_desc + ctx->pt0 * D, Ml, Bmat, w.ldb, MS, D, q, pref, Cmat, 2 * MS);
     MLFFPC_LAUNCH_CHECK();
-    MLFFPC_TRY(dgemm(false, Ml, D + 1, 2 * MS, 1.0, Cmat, 2 * MS, Bmat, w.ldb, 0.0, G, w.ldb, false, s));
+    MLFFPC_TRY(dgemm(false, Ml, D + 1, 2 * MS, 1.0, Cmat, 2 * MS, Bmat, w.ldb, 0.0, G, w.ldb, false, s, w.nsplit,
+                     Ml * w.ldb));
     int block = 32;
     while (block < 3 * N && block < 256) block <<= 1;
-    mv_epilogue_kernel<<<(unsigned)Ml, block, 0, s>>>(N, D, ctx->pt0, ctx->R_desc, ctx->R_d_desc, G, w.ldb, v, y_local, alpha, shift);
+    mv_epilogue_kernel<<<(unsigned)Ml, block, 0, s>>>(N, D, ctx->pt0, ctx->R_desc, ctx->R_d_desc, G, w.ldb, w.nsplit,
+                                                     Ml * w.ldb, v, y_local, alpha, shift);
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;
 }
