@@ -384,10 +384,28 @@ def run_ours(args):
               'precon_apply_avg_ms': pre_ms / max(op_calls, 1),
               'rel_resid_every_100_iters': [float('%.3g' % v) for v in tm['resid_hist_rel'][::100]]}
 
-    # ---- end-to-end arm: host numpy in, host numpy out, through Iterative.solve -----------------------
+    # ---- the same system through the matrix-free operator (one solve, reported next to the headline) ------
     del it, out
     task.pop('_K_buffer', None)
     torch.cuda.empty_cache()
+    alt = None
+    if args.mode != 'matrix_free' and not args.no_alt:
+        task_mf = dict(task)
+        task_mf['kernel_mode'] = 'matrix_free'
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        it_mf = Iterative(None, None)
+        out_mf = it_mf.solve_device(task_mf, eng, y_t, frac, 'cholesky', n_ind)
+        a1.record()
+        barrier()
+        alt = {'kernel_mode': 'matrix_free', 'value': max_over_ranks(a0.elapsed_time(a1) * 1e-3), 'unit': 's',
+               'cg_iters': int(out_mf[1]), 'converged': out_mf[3] == 0,
+               'matvec_avg_ms': it_mf.timings['pcg_stats']['op_ms'] / max(it_mf.timings['pcg_stats']['op_calls'], 1),
+               'note': 'same solve with the on-the-fly operator instead of the assembled kernel (one run, not the headline)'}
+        del it_mf, out_mf
+
+    # ---- end-to-end arm: host numpy in, host numpy out, through Iterative.solve -----------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h2d = d2h = 0
     res = None
@@ -422,6 +440,8 @@ def run_ours(args):
         'roofline': roofline,
         'phases': phases,
     }
+    if alt is not None:
+        line['alt'] = alt
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ref_iters = int(load_constants().get(args.workload, {}).get('cg_iters_reference_form', iters))
@@ -454,6 +474,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer arm (profiling runs)')
+    ap.add_argument('--no-alt', action='store_true', help='skip the extra matrix-free solve reported under "alt"')
     ap.add_argument('--tol', type=float, default=None, help='override the relative residual target (profiling runs)')
     ap.add_argument('--k', type=int, default=None, help='override the preconditioner rank')
     ap.add_argument('--precon-form', default=None, choices=['orthonormal', 'woodbury'])

@@ -66,6 +66,8 @@ struct GeoView {
     const int32_t* desc_perms;
     const int32_t* P;
     const int32_t* Pinv;
+    const int32_t* pair_a;  // [D] larger atom of descriptor d
+    const int32_t* pair_b;  // [D] smaller atom
 };
 
 static GeoView make_view(const mlffpc_ctx* c) {
@@ -75,6 +77,7 @@ static GeoView make_view(const mlffpc_ctx* c) {
     g.pref = 5.0 / (3.0 * c->sig * c->sig);
     g.R_desc = c->R_desc; g.R_d_desc = c->R_d_desc; g.Xp = c->Xp;
     g.desc_perms = c->desc_perms; g.P = c->atom_perms; g.Pinv = c->atom_perms_inv;
+    g.pair_a = c->pair_a; g.pair_b = c->pair_b;
     return g;
 }
 
@@ -219,22 +222,27 @@ __global__ void assemble_block_kernel(GeoView g, int64_t pt0, int64_t j_pt0, int
 
 
 // ---- explicit rows: one CTA = one row point i x up to JT column points ------------------------------------
-// Phase 1 builds, for every (column point, permutation) of the CTA, the difference vector, the coefficients
-// a_p / b_p and the two projected vectors u_i = J_i^T Delta, u_j = J_j^(p)T Delta in shared memory (all
-// threads busy: JT * S * 3N outputs).  Phase 2 gives every thread one OUTPUT COLUMN (point jj, atom A2,
+// Phase 1 builds, for every (column point jj, permutation p) =: q of the CTA, in shared memory
+//   dl[q][d]        = Delta_p = x_i - x_j^(p)                       -> a_p, b_p  (ab[q])
+//   ui[q][(A,c)]    = (J_i^T Delta)[(A,c)],   uj[q][(A2,c2)] = (J_j^(p)T Delta)[(A2,c2)]
+//   prod[q][d][c,c2] = sigma_p(d) g_i[d,c] g_j[e_p(d),c2]   with e_p(d) = pair(P[a_d], P[b_d]), sigma = +-1:
+//                      the 3x3 block of J_i^T J_j^(p) for the atom pair d = (A, Pinv[A2])
+//   gd[q][A2][c,c2]  = -sum_{B != A} prod[q][pair(A,B)][c,c2],  A = Pinv[A2]: the diagonal atom blocks
+//                      (translation invariance: every row of J sums to zero)
+// (all threads busy: JT * S * D * 9 products).  Phase 2 gives every thread one OUTPUT COLUMN (point jj, atom A2,
 // component c2) and lets it walk down the 3N rows, so a warp stores 32 consecutive doubles of one row of K --
-// full-sector coalesced writes, the HBM-write roofline of assembly.  All index arithmetic is hoisted out of the
-// row loop; the sparse Jacobian product J_i^T J_j is one multiply per off-diagonal atom pair and an (N-1)-term
-// sum on the diagonal atoms.
-// dynamic smem (doubles): xi[D] | gi[3D] | gj[JT][3D] | dl[JT][S][D] | ui[JT][S][3N] | uj[JT][S][3N] | ab[JT][S][2]
-//                         then ints: P[S][N] | Pinv[S][N]
+// full-sector coalesced writes, the HBM-write roofline of assembly; per entry it needs two shared loads and two
+// FMAs, no data-dependent branch or loop.
+// dynamic smem (doubles): xi[D] | gi[3D] | gj[JT][3D] | dl[JT S][D] | ui[JT S][3N] | uj[JT S][3N] | ab[JT S][2]
+//                         | gd[JT S][N][9] | prod[JT S][D][9]   then ints: P[S][N] | Pinv[S][N]
 constexpr int ASM_THREADS = 256;
 
+template <bool S1>
 __global__ void __launch_bounds__(ASM_THREADS)
 assemble_rows_kernel(GeoView g, int64_t i_pt0, int64_t j_pt0, int64_t n_jpts, int JT, int packed,
                      double* __restrict__ out, int64_t ld) {
     extern __shared__ double asm_sm[];
-    const int D = g.D, di = g.dim_i, S = g.S, N = g.N;
+    const int D = g.D, di = g.dim_i, S = S1 ? 1 : g.S, N = g.N;
     double* xi = asm_sm;
     double* gi = xi + D;
     double* gj = gi + 3 * D;
@@ -242,32 +250,48 @@ assemble_rows_kernel(GeoView g, int64_t i_pt0, int64_t j_pt0, int64_t n_jpts, in
     double* ui = dl + (size_t)JT * S * D;
     double* uj = ui + (size_t)JT * S * di;
     double* ab = uj + (size_t)JT * S * di;
-    int* P = (int*)(ab + (size_t)JT * S * 2);
+    double* gd = ab + (size_t)JT * S * 2;
+    double* prod = gd + (size_t)JT * S * N * 9;
+    int* P = (int*)(prod + (size_t)JT * S * D * 9);
     int* Pinv = P + S * N;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t il = blockIdx.x, i = i_pt0 + il;
     const int64_t jb = (int64_t)blockIdx.y * JT;
     const int nj = (int)((n_jpts - jb < JT) ? (n_jpts - jb) : JT);
+    const int nq = nj * S;
     // packed diagonal tile: band b of 256 rows keeps columns [0, 256 (b + 1)); skip CTAs entirely right of that
     if (packed && jb * di >= st_band_pitch(((il + 1) * di - 1) / ST_BAND_ROWS)) return;
 
     for (int t = tid; t < D; t += ASM_THREADS) xi[t] = g.R_desc[i * D + t];
     for (int t = tid; t < 3 * D; t += ASM_THREADS) gi[t] = g.R_d_desc[i * D * 3 + t];
     for (int t = tid; t < S * N; t += ASM_THREADS) { P[t] = g.P[t]; Pinv[t] = g.Pinv[t]; }
-    for (int t = tid; t < nj * 3 * D; t += ASM_THREADS) {
-        const int jj = t / (3 * D), e = t % (3 * D);
-        gj[(size_t)jj * 3 * D + e] = g.R_d_desc[(j_pt0 + jb + jj) * D * 3 + e];
+    for (int jj = 0; jj < nj; ++jj) {
+        const double* src = g.R_d_desc + (j_pt0 + jb + jj) * D * 3;
+        for (int e = tid; e < 3 * D; e += ASM_THREADS) gj[(size_t)jj * 3 * D + e] = src[e];
     }
     __syncthreads();
-    for (int t = tid; t < nj * S * D; t += ASM_THREADS) {
-        const int d = t % D, q = t / D;  // q = jj * S + p
-        const int64_t j = j_pt0 + jb + q / S;
-        dl[t] = xi[d] - g.Xp[(j * S + q % S) * (int64_t)D + d];
+    for (int q = 0; q < nq; ++q) {
+        const double* xj = g.Xp + ((j_pt0 + jb + q / S) * S + q % S) * (int64_t)D;
+        for (int d = tid; d < D; d += ASM_THREADS) dl[(size_t)q * D + d] = xi[d] - xj[d];
+    }
+    // prod[q][d][c,c2]: one thread per (q, d), 9 products each
+    for (int t = tid; t < nq * D; t += ASM_THREADS) {
+        const int d = t % D, q = t / D, p = q % S, jj = q / S;
+        const int a = g.pair_a[d], b = g.pair_b[d];  // a > b
+        const int Pa = P[p * N + a], Pb = P[p * N + b];
+        const int e = pair_index(Pa, Pb);
+        const double sg = (Pa < Pb) ? 1.0 : -1.0;
+        const double* gje = gj + (size_t)jj * 3 * D + e * 3;
+        const double g0 = sg * gi[d * 3], g1 = sg * gi[d * 3 + 1], g2 = sg * gi[d * 3 + 2];
+        double* o = prod + (size_t)t * 9;
+        o[0] = g0 * gje[0]; o[1] = g0 * gje[1]; o[2] = g0 * gje[2];
+        o[3] = g1 * gje[0]; o[4] = g1 * gje[1]; o[5] = g1 * gje[2];
+        o[6] = g2 * gje[0]; o[7] = g2 * gje[1]; o[8] = g2 * gje[2];
     }
     __syncthreads();
-    // a_p, b_p: one warp per (jj, p)
-    for (int q = warp; q < nj * S; q += ASM_THREADS / 32) {
+    // a_p, b_p: one warp per q
+    for (int q = warp; q < nq; q += ASM_THREADS / 32) {
         double s2 = 0.0;
         for (int d = lane; d < D; d += 32) { const double v = dl[(size_t)q * D + d]; s2 = fma(v, v, s2); }
         s2 = warp_sum(s2);
@@ -280,7 +304,7 @@ assemble_rows_kernel(GeoView g, int64_t i_pt0, int64_t j_pt0, int64_t n_jpts, in
     }
     // u_i[(A,c)] = sum_{B != A} sgn(A,B) g_i[pair(A,B), c] Delta[pair(A,B)]
     // u_j[(A2,c2)] = sum_{B != App} sgn(A2, P[B]) g_j[pair(A2, P[B]), c2] Delta[pair(App, B)],  App = Pinv[A2]
-    for (int t = tid; t < nj * S * di; t += ASM_THREADS) {
+    for (int t = tid; t < nq * di; t += ASM_THREADS) {
         const int r = t % di, q = t / di, p = q % S, jj = q / S;
         const int A = r / 3, c = r % 3;
         const double* dq = dl + (size_t)q * D;
@@ -304,37 +328,46 @@ assemble_rows_kernel(GeoView g, int64_t i_pt0, int64_t j_pt0, int64_t n_jpts, in
         ui[t] = a1;
         uj[t] = a2;
     }
+    // gd[q][A2][c,c2] = -sum_{B != A} prod[q][pair(A,B)][c,c2],  A = Pinv[A2]
+    for (int t = tid; t < nq * N * 9; t += ASM_THREADS) {
+        const int cc = t % 9, A2 = (t / 9) % N, q = t / (9 * N), p = q % S;
+        const int A = Pinv[p * N + A2];
+        const double* pq = prod + (size_t)q * D * 9 + cc;
+        double acc = 0.0;
+        for (int B = 0; B < N; ++B)
+            if (B != A) acc -= pq[pair_index(A, B) * 9];
+        gd[t] = acc;
+    }
     __syncthreads();
 
     // phase 2: thread <-> output column
     for (int col = tid; col < nj * di; col += ASM_THREADS) {
         const int jj = col / di, r2 = col % di, A2 = r2 / 3, c2 = r2 % 3;
-        const double* gjj = gj + (size_t)jj * 3 * D;
         const int64_t gcol = (jb + jj) * di + r2;  // column inside the tile
+        // S1: everything that does not depend on the row lives in registers
+        const int q1 = jj;
+        const int App1 = Pinv[A2];
+        const double auj1 = ab[2 * q1] * uj[(size_t)q1 * di + r2], b1 = ab[2 * q1 + 1];
+        const double* prod1 = prod + (size_t)q1 * D * 9 + c2;
+        const double* gd1 = gd + ((size_t)q1 * N + A2) * 9 + c2;
+        const double* ui1 = ui + (size_t)q1 * di;
         for (int A = 0; A < N; ++A) {
+            const double* pr1 = (A != App1) ? (prod1 + pair_index(A, App1) * 9) : gd1;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const int r = 3 * A + c;
-                double val = 0.0;
-                for (int p = 0; p < S; ++p) {
-                    const int q = jj * S + p;
-                    const int* Pp = P + p * N;
-                    const int App = Pinv[p * N + A2];
-                    double G;
-                    if (App != A) {
-                        const int PA = Pp[A];
-                        const double t = gi[pair_index(A, App) * 3 + c] * gjj[pair_index(PA, A2) * 3 + c2];
-                        G = ((A < App) == (A2 < PA)) ? t : -t;
-                    } else {
-                        G = 0.0;
-                        for (int B = 0; B < N; ++B) {
-                            if (B == A) continue;
-                            const int PB = Pp[B];
-                            const double t = gi[pair_index(A, B) * 3 + c] * gjj[pair_index(A2, PB) * 3 + c2];
-                            G += ((A < B) == (A2 < PB)) ? t : -t;
-                        }
+                double val;
+                if (S1) {
+                    val = fma(auj1, ui1[r], -b1 * pr1[c * 3]);
+                } else {
+                    val = 0.0;
+                    for (int p = 0; p < S; ++p) {
+                        const int q = jj * S + p;
+                        const int App = Pinv[p * N + A2];
+                        const double G = (App != A) ? prod[((size_t)q * D + pair_index(A, App)) * 9 + c * 3 + c2]
+                                                    : gd[((size_t)q * N + A2) * 9 + c * 3 + c2];
+                        val += ab[2 * q] * ui[(size_t)q * di + r] * uj[(size_t)q * di + r2] - ab[2 * q + 1] * G;
                     }
-                    val += ab[2 * q] * ui[(size_t)q * di + r] * uj[(size_t)q * di + r2] - ab[2 * q + 1] * G;
                 }
                 const int64_t row = il * di + r;
                 if (packed) {
@@ -350,7 +383,8 @@ assemble_rows_kernel(GeoView g, int64_t i_pt0, int64_t j_pt0, int64_t n_jpts, in
 
 static size_t assemble_rows_smem(const GeoView& g, int JT) {
     const size_t dbl = (size_t)g.D + 3 * g.D + (size_t)JT * 3 * g.D + (size_t)JT * g.S * g.D +
-                       2 * (size_t)JT * g.S * g.dim_i + (size_t)JT * g.S * 2;
+                       2 * (size_t)JT * g.S * g.dim_i + (size_t)JT * g.S * 2 + (size_t)JT * g.S * g.N * 9 +
+                       (size_t)JT * g.S * g.D * 9;
     return dbl * sizeof(double) + 2 * (size_t)g.S * g.N * sizeof(int) + 16;
 }
 
@@ -535,12 +569,19 @@ int assemble_tile(mlffpc_ctx* ctx, int64_t i_pt0, int64_t i_pt1, int64_t j_pt0, 
     int JT = ASM_THREADS / g.dim_i;
     if (JT > 8) JT = 8;
     if (JT < 1) JT = 1;
+    while (JT > 1 && assemble_rows_smem(g, JT) > 72 * 1024) --JT;  // keep >= 3 CTAs per SM when possible
     const size_t smem_rows = assemble_rows_smem(g, JT);
     const int64_t gy = (nj + JT - 1) / JT;
-    if (!ctx->assemble_legacy && smem_rows <= 160 * 1024 && gy <= 65535) {
-        MLFFPC_CUDA(cudaFuncSetAttribute(assemble_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
-        assemble_rows_kernel<<<dim3((unsigned)ni, (unsigned)gy), ASM_THREADS, smem_rows, s>>>(g, i_pt0, j_pt0, nj, JT, packed,
-                                                                                          out, ld);
+    if (!ctx->assemble_legacy && smem_rows <= 200 * 1024 && gy <= 65535) {
+        if (g.S == 1) {
+            MLFFPC_CUDA(cudaFuncSetAttribute(assemble_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+            assemble_rows_kernel<true><<<dim3((unsigned)ni, (unsigned)gy), ASM_THREADS, smem_rows, s>>>(g, i_pt0, j_pt0, nj, JT,
+                                                                                                    packed, out, ld);
+        } else {
+            MLFFPC_CUDA(cudaFuncSetAttribute(assemble_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+            assemble_rows_kernel<false><<<dim3((unsigned)ni, (unsigned)gy), ASM_THREADS, smem_rows, s>>>(g, i_pt0, j_pt0, nj, JT,
+                                                                                                     packed, out, ld);
+        }
         MLFFPC_LAUNCH_CHECK();
         return MLFFPC_OK;
     }

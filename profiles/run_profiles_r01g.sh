@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 T0=$(date +%s)
 stamp() { echo "[$(( $(date +%s) - T0 )) s] $*"; }
-B="python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline"
+B="python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-alt"
 NCU="ncu --clock-control none --profile-from-start off"
 WIN="assemble:0:1,pchol:3000:2,syrk:0:1,potrf:10:1,trsm:5:1,pcg:5:2"
 
