@@ -112,6 +112,13 @@ int mlffpc_symop_assemble(mlffpc_ctx* ctx, double* Ksym, void* stream);
 int mlffpc_symop_workspace_bytes(mlffpc_ctx* ctx, int64_t* bytes);
 int mlffpc_symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full, double* y_local, double alpha,
                        double shift, void* workspace, int64_t workspace_bytes, double* partial_out, void* stream);
+/* Library switches (all optional; defaults in brackets):
+ *   "symmetric_gemv"  [0]  mlffpc_pcg treats K_local as the symmetric tile storage
+ *   "layout_world", "layout_rank"   tile partition override (rank emulation on one GPU)
+ *   "pchol_lookahead" [1]  blocked pivoted Cholesky with a candidate panel (0 = plain left-looking build)
+ *   "assemble_legacy" [0]  first-generation assembly kernel (one CTA per 3N x 3N block)
+ *   diagnostics for the numerics study in DESIGN.md: "precon_accuracy" (1 Kahan, 2 two-halves summation of T r),
+ *   "tgemv_msplit" (1/4/8), "dot_split" (1..8), "syrk_chunk" (> 0: Gram by Kahan-summed column chunks) */
 int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value);
 
 /* Matrix-free matvec  y_local = alpha * (K v)_local + shift * v_local, v is the full n-vector.
