@@ -311,9 +311,15 @@ int symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full, doubl
 
 int symop_assemble(mlffpc_ctx* ctx, double* Ksym, cudaStream_t s) {
     const std::vector<SymTile> tiles = symop_plan(ctx, nullptr);
-    for (const auto& t : tiles)
-        MLFFPC_TRY(assemble_tile(ctx, t.i_pt0, t.i_pt1, t.j_pt0, t.j_pt1, Ksym + t.off, t.ld, t.diag ? 1 : 0, s));
-    return MLFFPC_OK;
+    ProfWindow pw = prof_window("assemble");
+    pw.step(pw.first);
+    int st = MLFFPC_OK;
+    for (const auto& t : tiles) {
+        st = assemble_tile(ctx, t.i_pt0, t.i_pt1, t.j_pt0, t.j_pt1, Ksym + t.off, t.ld, t.diag ? 1 : 0, s);
+        if (st != MLFFPC_OK) break;
+    }
+    pw.end();
+    return st;
 }
 
 }  // namespace mlffpc
