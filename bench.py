@@ -236,7 +236,10 @@ def workload_config(inp, args, world):
                         % (args.workload, inp['kind'], inp['N'], inp['M'], inp['n'], storage, world, inp['k'], inp['tol']),
             'kernel_mode': args.mode, 'precon_form': args.precon_form or 'orthonormal', 'n': inp['n'], 'k': inp['k'],
             'tol': inp['tol'],
-            'l2_policy': 'inputs larger than L2: K (>= 11.7 GB per GPU) is re-assembled and streamed every step'}
+            'l2_policy': 'inputs larger than L2 (126 MB): every CG iteration streams this rank\'s %.1f GB of K and %.1f GB '
+                         'of the preconditioner factor once; K is re-assembled every step'
+                         % ({'assembled': 8.0, 'assembled_sym': 4.0, 'matrix_free': 0.0}[args.mode] * inp['n'] ** 2 / world / 1e9,
+                            16.0 * inp['k'] * inp['n'] / world / 1e9)}
 
 
 # ----------------------------------------------------------------------------- GPU arm
