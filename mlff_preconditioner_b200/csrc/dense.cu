@@ -1,5 +1,7 @@
 // fp64 dense building blocks on the DMMA pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has
 // no fp64 kind on sm_100): row-major GEMM, SYRK over long rows, blocked Cholesky, blocked row-TRSM.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mlffpc {
@@ -47,7 +49,7 @@ struct GemmSmem {
 };
 
 template <int BM, int BN, int WARPS_M, int WARPS_N, bool TRANSB, bool VEC2>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32)
 dgemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __restrict__ A, int64_t lda,
              const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C, int64_t ldc,
              int lower_only, int64_t k_chunk, int64_t c_zstride) {
@@ -64,7 +66,7 @@ dgemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __rest
     using SM = GemmSmem<BM, BN, TRANSB>;
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;  // warp tile
     constexpr int TM = WM / 8, TN = WN / 8;              // 8x8 mma tiles per warp
-    static_assert(WARPS_M * WARPS_N * 32 == GEMM_THREADS, "8 warps");
+    constexpr int NT = WARPS_M * WARPS_N * 32;  // 8 warps (64x32 or 32x64 warp tiles) or 16 warps (32x32)
     extern __shared__ double smem[];
 
     const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
@@ -89,7 +91,7 @@ dgemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __rest
         constexpr int V = VEC2 ? 2 : 1;
         // A tile: BM x BK, k contiguous
         constexpr int A_ITEMS = BM * GEMM_BK / V;
-        for (int t = tid; t < A_ITEMS; t += GEMM_THREADS) {
+        for (int t = tid; t < A_ITEMS; t += NT) {
             const int r = t / (GEMM_BK / V), c = (t % (GEMM_BK / V)) * V;
             const bool ok = (m0 + r < m) && (k0 + c < k);
             const double* src = ok ? (A + (m0 + r) * lda + k0 + c) : A;
@@ -98,7 +100,7 @@ dgemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __rest
         }
         if (TRANSB) {  // B[n, k], k contiguous -> Bs[BN][BK+4]
             constexpr int B_ITEMS = BN * GEMM_BK / V;
-            for (int t = tid; t < B_ITEMS; t += GEMM_THREADS) {
+            for (int t = tid; t < B_ITEMS; t += NT) {
                 const int r = t / (GEMM_BK / V), c = (t % (GEMM_BK / V)) * V;
                 const bool ok = (n0 + r < n) && (k0 + c < k);
                 const double* src = ok ? (B + (n0 + r) * ldb + k0 + c) : B;
@@ -107,7 +109,7 @@ dgemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double* __rest
             }
         } else {  // B[k, n], n contiguous -> Bs[BK][BN+4]
             constexpr int B_ITEMS = GEMM_BK * BN / V;
-            for (int t = tid; t < B_ITEMS; t += GEMM_THREADS) {
+            for (int t = tid; t < B_ITEMS; t += NT) {
                 const int r = t / (BN / V), c = (t % (BN / V)) * V;
                 const bool ok = (k0 + r < k) && (n0 + c < n);
                 const double* src = ok ? (B + (k0 + r) * ldb + n0 + c) : B;
@@ -181,7 +183,7 @@ static int launch_dgemm(int64_t m, int64_t n, int64_t k, double alpha, const dou
     // chunks are multiples of the k tile and even, so 16-byte staging stays aligned in every slice
     int64_t k_chunk = (k + nsplit - 1) / nsplit;
     k_chunk = (k_chunk + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
-    kern<<<grid, GEMM_THREADS, SM::BYTES, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0, k_chunk,
+    kern<<<grid, WARPS_M * WARPS_N * 32, SM::BYTES, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0, k_chunk,
                                                c_zstride);
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;
@@ -195,9 +197,13 @@ int dgemm(bool transB, int64_t m, int64_t n, int64_t k, double alpha, const doub
     const bool vec2 = (lda % 2 == 0) && (ldb % 2 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
     const bool narrow = (n <= 64);
     const bool flat = (m <= 64) && !narrow;  // few rows, many columns (the look-ahead panel update, TRSM tails)
+    // experimental: 16 warps with 32x32 warp tiles on the 128x128 tile (twice the warps per SM to cover the
+    // shared-load -> DMMA latency); selected with MLFFPC_DGEMM16=1 until it is measured against the 8-warp kernel
+    static const bool warps16 = [] { const char* e = getenv("MLFFPC_DGEMM16"); return e && e[0] == '1'; }();
 #define MLFFPC_GEMM_DISPATCH(TB, V2)                                                                      \
     (narrow ? launch_dgemm<128, 64, 4, 2, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride) \
      : flat ? launch_dgemm<64, 128, 2, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride) \
+     : warps16 ? launch_dgemm<128, 128, 4, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride) \
             : launch_dgemm<128, 128, 2, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride))
     if (transB) return vec2 ? MLFFPC_GEMM_DISPATCH(true, true) : MLFFPC_GEMM_DISPATCH(true, false);
     return vec2 ? MLFFPC_GEMM_DISPATCH(false, true) : MLFFPC_GEMM_DISPATCH(false, false);
