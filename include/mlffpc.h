@@ -117,6 +117,8 @@ int mlffpc_symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full
  *   "layout_world", "layout_rank"   tile partition override (rank emulation on one GPU)
  *   "pchol_lookahead" [1]  blocked pivoted Cholesky with a candidate panel (0 = plain left-looking build)
  *   "assemble_legacy" [0]  first-generation assembly kernel (one CTA per 3N x 3N block)
+ *   "precon_reorth"   [0]  EXPERIMENTAL: project the complement twice in the orthonormal-form preconditioner apply
+ *                          (two more passes over the factor; removes the 1/lam leak of Qt Qt^T - I)
  *   diagnostics for the numerics study in DESIGN.md: "precon_accuracy" (1 Kahan, 2 two-halves summation of T r),
  *   "tgemv_msplit" (1/4/8), "dot_split" (1..8), "syrk_chunk" (> 0: Gram by Kahan-summed column chunks) */
 int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value);

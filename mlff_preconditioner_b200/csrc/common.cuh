@@ -91,6 +91,11 @@ struct mlffpc_ctx {
     // partition used by the symmetric tile operator; follows the communicator unless overridden by the
     // options "layout_rank"/"layout_world" (rank emulation on one GPU, tests only)
     int lay_rank = 0, lay_world = 1;
+    // option "precon_reorth" (experimental, off): project the complement twice in the orthonormal-form apply; the
+    // scratch (n_local + k doubles) is allocated by the library when the option is switched on
+    bool precon_reorth = false;
+    double* reorth_scratch = nullptr;
+    int64_t reorth_scratch_len = 0;
     bool assemble_legacy = false;  // option "assemble_legacy": one CTA per 3N x 3N block (the first-generation kernel)
     int64_t syrk_chunk = 0;        // option "syrk_chunk": > 0 = Gram matrices by column chunks with Kahan-summed partials
     int tgemv_msplit = 0;          // option "tgemv_msplit": force the row split of T^T u (1, 4, 8; 0 = auto)
@@ -176,6 +181,7 @@ int matvec_free(mlffpc_ctx* ctx, const double* v, double* y_local, double alpha,
 int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
                  const double* r, double* z, double* u, cudaStream_t s, const double* Mk = nullptr);
 
+int ensure_reorth_scratch(mlffpc_ctx* ctx, int64_t k);
 // internal dense building blocks (dense.cu), all on `s`
 // nsplit > 1: split-K, slice z writes its partial product to C + z * c_zstride (beta applies to every slice)
 int dgemm(bool transB, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,

@@ -174,6 +174,7 @@ int mlffpc_destroy(mlffpc_ctx* ctx) {
     if (ctx->scal) cudaFree(ctx->scal);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->partials) cudaFree(ctx->partials);
+    if (ctx->reorth_scratch) cudaFree(ctx->reorth_scratch);
     delete ctx;
     return MLFFPC_OK;
 }
@@ -215,6 +216,10 @@ int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value) {
     const std::string nm(name);
     if (nm == "symmetric_gemv") { ctx->use_symv = value != 0; return MLFFPC_OK; }
     if (nm == "tgemv_msplit") { ctx->tgemv_msplit = (value == 1 || value == 4 || value == 8) ? (int)value : 0; return MLFFPC_OK; }
+    if (nm == "precon_reorth") {
+        ctx->precon_reorth = value != 0;
+        return MLFFPC_OK;
+    }
     if (nm == "assemble_legacy") { ctx->assemble_legacy = value != 0; return MLFFPC_OK; }
     if (nm == "syrk_chunk") { ctx->syrk_chunk = value > 0 ? value : 0; return MLFFPC_OK; }
     if (nm == "dot_split") { ctx->dot_split = value >= 1 && value <= 8 ? (int)value : 1; return MLFFPC_OK; }

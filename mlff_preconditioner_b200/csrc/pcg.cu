@@ -172,6 +172,7 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     MLFFPC_REQUIRE(!ctx->use_symv || ctx->lay_world == ctx->comm.world, "pcg: symmetric tile layout does not match the communicator");
     MLFFPC_REQUIRE(!T || (k > 0 && ld_t >= ctx->n_local()), "pcg: bad preconditioner dimensions");
     const bool matrix_free = (K_local == nullptr);
+    if (T && Mk) MLFFPC_TRY(ensure_reorth_scratch(ctx, k));
     const PcgWs w = pcg_layout(ctx, T ? k : 0, matrix_free);
     MLFFPC_REQUIRE(workspace_bytes >= w.total, "pcg: workspace too small (%lld < %lld)",
                    (long long)workspace_bytes, (long long)w.total);

@@ -12,6 +12,19 @@ __global__ void add_inplace_kernel(double* __restrict__ a, const double* __restr
     if (t < n) a[t] += b[t];
 }
 
+// scratch of the twice-projected apply: owned by the context, (re)allocated when the shapes grow
+int ensure_reorth_scratch(mlffpc_ctx* ctx, int64_t k) {
+    if (!ctx->precon_reorth) return MLFFPC_OK;
+    const int64_t need = ((ctx->n_local() + 31) / 32 * 32) + k + 64;
+    if (ctx->reorth_scratch_len >= need) return MLFFPC_OK;
+    if (ctx->reorth_scratch) cudaFree(ctx->reorth_scratch);
+    ctx->reorth_scratch = nullptr;
+    ctx->reorth_scratch_len = 0;
+    MLFFPC_CUDA(cudaMalloc((void**)&ctx->reorth_scratch, (size_t)need * sizeof(double)));
+    ctx->reorth_scratch_len = need;
+    return MLFFPC_OK;
+}
+
 // u: device scratch of 2 k + 4 doubles.  Mk == NULL: Woodbury form z = sign (r - T^T T r) / lam.
 // Mk != NULL: T holds an orthonormal basis Q^T of range(L) and Mk = (Q^T L L^T Q + lam I)^{-1}:
 //   z = sign ( (r - Q (Q^T r)) / lam + Q Mk (Q^T r) ).
@@ -32,6 +45,23 @@ int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double
         MLFFPC_TRY(launch_gemv_rows(T, k, nl, ld, r, u, 1.0, 0.0, 0, s, comp));
     }
     MLFFPC_TRY(comm_allreduce_sum(ctx->comm, u, (size_t)k, s));
+    if (Mk && ctx->precon_reorth && ctx->reorth_scratch) {
+        // Orthonormal form with the complement projected twice ("twice is enough"): Qt Qt^T = I + E with
+        // |E| ~ 1e-16 sqrt(n), and (I - Qt^T Qt) a / lam leaks E / lam ~ 1e-4 of a range vector back into the
+        // range.  rp = (I - Qt^T Qt)^2 r removes the leak; z = rp / lam + Qt^T Mk (w + w2).  Same kernels, two
+        // more passes over the factor.  (CPU experiment: profiles/r01v_precon_forms_cpu.txt.)
+        double* rp = ctx->reorth_scratch;       // n_local doubles
+        double* w2 = u + k + 2;
+        MLFFPC_TRY(launch_tgemv_cols(T, k, nl, ld, u, rp, 1, r, 1.0, ctx->num_sms, s, false, ctx->tgemv_msplit));  // rp = r - Qt^T w
+        MLFFPC_TRY(launch_gemv_rows(T, k, nl, ld, rp, w2, 1.0, 0.0, 0, s, false));                                   // w2 = Qt rp
+        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, w2, (size_t)k, s));
+        add_inplace_kernel<<<(unsigned)((k + 255) / 256), 256, 0, s>>>(u, w2, k);                                   // u = w + w2
+        MLFFPC_LAUNCH_CHECK();
+        double* mu = ctx->reorth_scratch + ((nl + 31) / 32 * 32);  // k doubles
+        MLFFPC_TRY(launch_gemv_rows(Mk, k, k, k, u, mu, 1.0, 0.0, 0, s, false));                                     // mu = Mk (w + w2)
+        // z = sign ((rp - Qt^T w2) / lam + Qt^T mu)
+        return launch_tgemv_cols(T, k, nl, ld, w2, z, 1, rp, sign / lam, ctx->num_sms, s, false, ctx->tgemv_msplit, mu, sign);
+    }
     if (Mk) {
         double* u2 = u + k + 2;
         MLFFPC_TRY(launch_gemv_rows(Mk, k, k, k, u, u2, 1.0, 0.0, 0, s, false));  // replicated k x k product
@@ -155,6 +185,7 @@ int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld,
         return MLFFPC_OK;
     }
     MLFFPC_REQUIRE(u && ld >= ctx->n_local(), "precon_apply: bad argument");
+    if (Mk) MLFFPC_TRY(ensure_reorth_scratch(ctx, k));
     return precon_apply(ctx, T, k, ld, lam, sign, r, z, u, s, Mk);
 }
 

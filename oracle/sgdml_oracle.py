@@ -271,6 +271,28 @@ def woodbury_apply(T, lam, a):
     return (1.0 / lam) * (a - T.T @ (T @ a))
 
 
+def orthonormal_factor(L, lam):
+    """The same inverse ``(L L^T + lam I)^{-1}`` in an orthonormal basis -- numpy restatement of
+    ``mlffpc_orthonormal_factor`` (csrc/precon.cu; not in the reference, which only has the Woodbury form above).
+    CholeskyQR2: ``L^T = C1 C2 Qt`` with ``Qt Qt^T = I``; ``Mk = (B^T B + lam I)^{-1}``, ``B = C1 C2``.
+    Returns ``(Qt[k, n], Mk[k, k])``."""
+    Lt = np.array(L.T, dtype=float)
+    C1 = scipy.linalg.cholesky(Lt @ Lt.T, lower=True)
+    Lt = scipy.linalg.solve_triangular(C1, Lt, lower=True)
+    C2 = scipy.linalg.cholesky(Lt @ Lt.T, lower=True)
+    Qt = scipy.linalg.solve_triangular(C2, Lt, lower=True)
+    B = C1 @ C2
+    S = B.T @ B + lam * np.eye(B.shape[0])
+    Y = scipy.linalg.solve_triangular(scipy.linalg.cholesky(S, lower=True), np.eye(B.shape[0]), lower=True)
+    return Qt, Y.T @ Y
+
+
+def orthonormal_apply(Qt, Mk, lam, a):
+    """``(a - Qt^T Qt a) / lam + Qt^T Mk Qt a``."""
+    w = Qt @ a
+    return (a - Qt.T @ w) / lam + Qt.T @ (Mk @ w)
+
+
 def cho_factor_stable(Mat):
     """Upper Cholesky factor after the +-1e-15 diagonal nudge (solvers/iterative_solver.py:576-583).
     Returns the clean upper-triangular factor (the reference keeps LAPACK's full array + a flag)."""
