@@ -293,6 +293,16 @@ def orthonormal_apply(Qt, Mk, lam, a):
     return (a - Qt.T @ w) / lam + Qt.T @ (Mk @ w)
 
 
+def orthonormal_apply_reorth(Qt, Mk, lam, a):
+    """Orthonormal form with the complement projected twice (library option ``precon_reorth``, csrc/precon.cu):
+    ``rp = (I - Qt^T Qt)^2 a``,  ``z = rp / lam + Qt^T Mk (Qt a + Qt rp1)`` with ``rp1`` the first projection."""
+    w = Qt @ a
+    rp = a - Qt.T @ w
+    w2 = Qt @ rp
+    rp = rp - Qt.T @ w2
+    return rp / lam + Qt.T @ (Mk @ (w + w2))
+
+
 def cho_factor_stable(Mat):
     """Upper Cholesky factor after the +-1e-15 diagonal nudge (solvers/iterative_solver.py:576-583).
     Returns the clean upper-triangular factor (the reference keeps LAPACK's full array + a flag)."""
