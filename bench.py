@@ -318,7 +318,24 @@ def run_ours(args):
         out = it.solve_device(task, eng, y_t, frac, 'cholesky', n_ind)
         return it, out
 
-    for _ in range(args.warmup):
+    # Probe solve before anything is timed: the twice-projected apply was validated on one GPU only when this
+    # was written; if it does not converge here (every rank sees the same numbers, so every rank takes the same
+    # branch) the benchmark falls back to the plain orthonormal form and says so in the JSON line.
+    reorth_fallback = None
+    probe_ok = False
+    if task['_options'].get('precon_reorth') and args.warmup > 0:   # --warmup 0 (profiling / A-B runs): no probe
+        try:
+            _, probe = one_step()
+            if probe[3] != 0:
+                reorth_fallback = 'probe solve did not converge (info = %d)' % probe[3]
+        except Exception as exc:  # noqa: BLE001
+            reorth_fallback = '%s: %s' % (type(exc).__name__, exc)
+        if reorth_fallback:
+            task['_options']['precon_reorth'] = 0
+            eng.set_option('precon_reorth', 0)
+        else:
+            probe_ok = True      # a full solve on the final path: it is the first warm-up step
+    for _ in range(max(args.warmup - (1 if probe_ok else 0), 0)):
         one_step()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -451,6 +468,8 @@ def run_ours(args):
     }
     if alt is not None:
         line['alt'] = alt
+    if reorth_fallback:
+        line['config']['precon_form'] = (args.precon_form or 'orthonormal') + ' (precon_reorth fell back: %s)' % reorth_fallback
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ref_iters = int(load_constants().get(args.workload, {}).get('cg_iters_reference_form', iters))
