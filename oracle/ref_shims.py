@@ -12,6 +12,8 @@ import types
 import numpy as np
 
 REFERENCE_SGDML = '/root/reference/src/sGDML'
+# when a list is assigned here, legacy_cg appends ||r|| after every iteration (golden generation only)
+RESID_HISTORY = None
 
 
 def legacy_cg(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, atol=None):
@@ -61,6 +63,8 @@ def legacy_cg(A, b, x0=None, tol=1e-5, maxiter=None, M=None, callback=None, atol
         if resid <= atol_eff and it > 1:
             r = b - A.matvec(x)
             resid = float(np.linalg.norm(r))
+        if RESID_HISTORY is not None:
+            RESID_HISTORY.append(resid)
         if resid <= atol_eff:
             info = 0
             break

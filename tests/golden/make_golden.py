@@ -169,7 +169,80 @@ def case_large_cholesky(name, kind, M, seed, frac, tol):
     print('wrote', name, 'n =', n, 'iters', num_iters, 'resid %.3e' % resid, 'conv', is_conv)
 
 
+def case_cfg1_solve(name='cfg1_nanotube_m9', frac_k=None):
+    """BASELINE.json configs[0] at full size: nanotube-size N = 370, M = 9, n = 9990, k = 1954 (rule of thumb),
+    tol 1e-6, one run of the unmodified ``Iterative.solve(str_preconditioner='cholesky')`` (about 7 minutes on 8
+    cores).  The factor, the preconditioner operator and the residual history are captured by wrapping the
+    reference's own callables at run time (nothing is modified)."""
+    from bench import make_inputs
+    inp = make_inputs('cfg1')
+    n, k, M, N = inp['n'], inp['k'], inp['M'], inp['N']
+    ds = synthetic.make_dataset(inp['kind'], M + 2, seed=0)
+    perms = inp['perms']
+    task = ref_shims.make_task(sgdml, ds, M, perms, sig=SIG, solver_tol=inp['tol'])
+    task['lam'] = LAM
+    desc = Desc(N, max_processes=1)
+    R_desc, R_d_desc, tpl, y, y_std = inp['R_desc'], inp['R_d_desc'], inp['tpl'], inp['y'], inp['y_std']
+    # the repo's host Desc against the reference's (the GPU test regenerates the descriptors from R_train)
+    Rd_ref, Rdd_ref = desc.from_R(task['R_train'].reshape(M, -1), callback=noop)
+    assert np.abs(Rd_ref - R_desc).max() <= 1e-15 * np.abs(Rd_ref).max()
+    assert np.abs(Rdd_ref - R_d_desc).max() <= 1e-14 * np.abs(Rdd_ref).max()
+    R_desc, R_d_desc = Rd_ref, Rdd_ref
+    captured = {}
+    orig_pc = ichol.pivoted_cholesky
+
+    def pc_capture(*a, **kw):
+        res = orig_pc(*a, **kw)
+        captured['L'], captured['index_columns'] = res[0], res[1]
+        return res
+
+    orig_init = IterativeCholesky._init_precon_operator
+
+    def init_capture(self, *a, **kw):
+        res = orig_init(self, *a, **kw)
+        captured['P_op'] = res[0]
+        return res
+
+    ichol.pivoted_cholesky = pc_capture
+    IterativeCholesky._init_precon_operator = init_capture
+    ref_shims.RESID_HISTORY = []
+    try:
+        it = Iterative(GT, desc, callback=noop, use_torch=True)
+        frac = (k + 0.5) / n
+        alphas, num_iters, resid, rmse, ind, is_conv, info = it.solve(
+            task, R_desc, R_d_desc, tpl, y, y_std, break_percentage=frac, str_preconditioner='cholesky')
+    finally:
+        ichol.pivoted_cholesky = orig_pc
+        IterativeCholesky._init_precon_operator = orig_init
+    hist = np.array(ref_shims.RESID_HISTORY)
+    ref_shims.RESID_HISTORY = None
+    L = captured['L']
+    assert L.shape == (n, k) and np.array_equal(captured['index_columns'], info['index_columns'])
+    rng = np.random.default_rng(11)
+    rows = np.sort(rng.choice(n, size=48, replace=False))
+    colsel = np.array([0, 1, 2, k // 4, k // 2, k - 2, k - 1])
+    a = rng.standard_normal(n)
+    v = rng.standard_normal(n)
+    K_op = it._init_kernel_operator(task, R_desc, R_d_desc, tpl, LAM, n, callback=noop)
+    K_op_v = K_op.matvec(v)
+    itc = IterativeCholesky(gdml_train=GT, desc=desc, task=task, callback=noop, use_torch=True)
+    diag = itc._assemble_kernel_mat_diag(tril_perms_lin=tpl, sig=SIG, R_desc=R_desc, R_d_desc=R_d_desc, n=n)
+    pcols = np.sort(rng.choice(n, size=24, replace=False))
+    K_panel = GT._assemble_kernel_mat(R_desc, R_d_desc, tpl, SIG, desc, col_idxs=pcols, callback=noop).copy()
+    out = dict(kind=inp['kind'], M=M, N=N, perms=perms, sig=SIG, lam=LAM, R_train=task['R_train'],
+               F_train=task['F_train'], y=y, y_std=y_std, chol_k=k, frac=frac, tol=inp['tol'], alphas=alphas,
+               num_iters=num_iters, resid=resid, is_conv=is_conv, index_columns=info['index_columns'],
+               resid_hist=hist, L_rows=rows, L_sample=L[rows, :], L_cols=colsel, L_colsample=L[:, colsel],
+               L_colnorm=np.linalg.norm(L, axis=0), a=a, P_chol_a=captured['P_op'].matvec(a), v=v, K_op_v=K_op_v,
+               diag=diag, panel_cols=pcols, K_panel=K_panel)
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print('wrote', name, 'n =', n, 'k =', k, 'iters', num_iters, 'resid %.3e' % resid, 'conv', is_conv)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'cfg1':
+        case_cfg1_solve()
+        sys.exit(0)
     id9 = np.arange(9)[None]
     all_strs = ('cholesky', 'random_scores', 'lev_scores', 'inverse_lev', 'lev_random',
                 'truncated_cholesky', 'truncated_cholesky_custom')
