@@ -128,11 +128,30 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------- CPU arm
+def _cpu_threads():
+    """All host threads for torch, numpy's BLAS and LAPACK -- explicitly, because torchrun exports OMP_NUM_THREADS=1."""
+    import torch
+
+    ncores = os.cpu_count() or 1
+    try:
+        torch.set_num_threads(ncores)
+    except RuntimeError:
+        pass
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=ncores)
+    except Exception:
+        pass
+    return ncores
+
+
 def cpu_reference_sample(inp, cg_iters, light=False):
     """Bounded sample of the reference's CPU algorithm on this box, extrapolated to one full solve.
 
-    Per-operation costs are measured with the oracle port of the reference (oracle/sgdml_oracle.py; the
-    kernel matvec through torch-CPU ops exactly like the reference's use_torch=True path without a GPU):
+    Per-operation costs are measured with the oracle port of the reference (oracle/sgdml_oracle.py); the kernel matvec
+    runs the reference's torch-CPU op sequence from the Cartesian geometries (torchtools.py:172-272, one 32 GB batch)
+    and costs what the reference's own K_op.matvec costs on the same cores (tests/test_cpu_arm_cost.py):
       t_mv   one K_op.matvec at full n                       (also the cost of one pivot column: get_col = K_op e_i)
       t_sch  one pivot step's Schur update at m = k/2         (incomplete_cholesky.py:66-78)
       t_fac  Woodbury factorisation at rank k' << k, scaled by (k/k')^2   (iterative_cholesky.py:141-143)
@@ -142,18 +161,21 @@ def cpu_reference_sample(inp, cg_iters, light=False):
     import torch
     from oracle import sgdml_oracle as orc
 
-    torch.set_num_threads(os.cpu_count())
+    _cpu_threads()
     n, k, M = inp['n'], inp['k'], inp['M']
     rng = np.random.default_rng(0)
-    R_desc_t = torch.from_numpy(inp['R_desc'])
-    Xp_t = torch.from_numpy(orc.permuted_rows(inp['R_desc'], inp['tpl']).reshape(-1, inp['R_desc'].shape[1]))
+    D = inp['R_desc'].shape[1]
+    Rs_t = torch.from_numpy(np.ascontiguousarray(inp['task']['R_train'], dtype=np.float64))
+    Xp_t = torch.from_numpy(np.ascontiguousarray(orc.permuted_rows(inp['R_desc'], inp['tpl']).reshape(-1, D)))
     v = rng.standard_normal(n)
-    reps_mv = 1 if light else 2
-    orc.kernel_matvec_torch_cpu(R_desc_t, Xp_t, inp['R_d_desc'], inp['tpl'], 10, v[:n])  # warm
-    t0 = time.perf_counter()
+    reps_mv = 1 if light else 3
+    orc.kernel_matvec_torch_cpu(Rs_t, Xp_t, inp['R_d_desc'], inp['tpl'], 10, v)  # warm (thread pools, page faults)
+    ts = []
     for _ in range(reps_mv):
-        orc.kernel_matvec_torch_cpu(R_desc_t, Xp_t, inp['R_d_desc'], inp['tpl'], 10, v)
-    t_mv = (time.perf_counter() - t0) / reps_mv
+        t0 = time.perf_counter()
+        orc.kernel_matvec_torch_cpu(Rs_t, Xp_t, inp['R_d_desc'], inp['tpl'], 10, v)
+        ts.append(time.perf_counter() - t0)
+    t_mv = float(np.median(ts))
 
     m_half = max(1, k // 2 if not light else k // 8)
     L = np.ones((n, m_half))
@@ -185,6 +207,11 @@ def cpu_reference_sample(inp, cg_iters, light=False):
     return total, detail
 
 
+CPU_SAMPLE_TEXT = ("3 full-n kernel matvecs in the reference's torch-CPU op sequence (median), 2 Schur-update steps at m=k/2, "
+                   "Woodbury factor at k'=512 (scaled (k/k')^2), 3 applies at k' (scaled k/k'); "
+                   'extrapolated solve = k(t_mv+t_sch)+t_fac+iters(t_mv+t_app)')
+
+
 def load_constants():
     try:
         return json.load(open(CONSTANTS_FILE))
@@ -192,15 +219,31 @@ def load_constants():
         return {}
 
 
+def reference_iteration_count(workload, fallback):
+    """CG iterations of the reference's own formula on this workload and where the number comes from: measured with the
+    unmodified reference (cfg1), with the oracle port on the CPU (cfg2, when the run is recorded), else the device's
+    count with precon_form='woodbury' (same formula, same pivots) -- never the projected form's smaller count."""
+    c = load_constants().get(workload, {})
+    for key, label in (('cg_iters_reference_measured', 'unmodified reference, CPU'),
+                       ('cg_iters_port_measured', 'oracle port of the reference formula, CPU'),
+                       ('cg_iters_gpu_woodbury_form', "device run with the reference's formula (precon_form=woodbury)")):
+        if key in c:
+            return int(c[key]), '%s (%s)' % (label, c.get(key + '_source', 'bench_constants.json'))
+    return int(fallback), 'assumed (no recorded run of the reference formula for this workload)'
+
+
+def measured_cpu_points(workload):
+    """Fully measured (not extrapolated) CPU solves recorded for this workload, for context next to the sample."""
+    return load_constants().get(workload, {}).get('measured_full_solves', [])
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     inp = make_inputs(args.workload, args.M, args.tol, args.k)
-    consts = load_constants().get(args.workload, {})
-    cg_iters = int(consts.get('cg_iters_reference_form', 1000))
-    src = ('bench_constants.json (measured on B200 with the reference\'s Woodbury formula, precon_form=woodbury)'
-           if 'cg_iters_reference_form' in consts else 'assumed (no GPU run recorded yet)')
+    cg_iters, src = reference_iteration_count(args.workload, 1000)
+    ncores = _cpu_threads()
     for _ in range(args.warmup):
         cpu_reference_sample(inp, cg_iters, light=True)
     vals, detail = [], None
@@ -210,20 +253,29 @@ def run_reference_arm(args):
         vals.append(v)
     wall = time.perf_counter() - t_wall
     value = float(np.mean(vals))
-    sample = ('per step: 2 full-n torch-CPU kernel matvecs, 2 Schur-update steps at m=k/2, Woodbury factor at k\'=512 '
-              '(scaled (k/k\')^2), 3 applies at k\' (scaled k/k\'); extrapolated solve = k(t_mv+t_sch)+t_fac+iters(t_mv+t_app); '
-              'cg_iters=%d from %s' % (cg_iters, src))
+    sample = 'per step: %s; cg_iters=%d from %s' % (CPU_SAMPLE_TEXT, cg_iters, src)
     line = {
         'impl': 'reference', 'metric': 'pcg_time_to_solution', 'value': value, 'unit': 's', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / max(args.steps, 1),
         'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(inp, args, 1),
-        'cpu_baseline': {'value': value, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample,
-                         'extrapolated': True, 'detail': detail},
+        'config': workload_config(inp, args, max(args.gpus, 1)),
+        'cpu_baseline': {'value': value, 'unit': 's', 'cores': ncores, 'kind': 'port', 'sample': sample,
+                         'extrapolated': True, 'detail': detail,
+                         'measured_full_solves': measured_cpu_points(args.workload)},
         'e2e': {'value': value, 'unit': 's', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
+
+
+PRECON_FORM_TEXT = {
+    'projected': "projected: orthonormal basis of range(L) + k x k inverse + first-order exact complement projector "
+                 "(E = Qt Qt^T - I from the extended-precision DMMA Gram), two passes over the factor per apply; same "
+                 "operator as the reference's Woodbury formula, no 1/lam cancellation",
+    'woodbury': "woodbury: the reference's formula (iterative_cholesky.py:141-148), Gram summed in extended precision",
+    'orthonormal': 'orthonormal: projected form without the defect correction (round-1 form)',
+    'reorth': 'orthonormal + complement projected twice (four passes over the factor; option precon_reorth=1)',
+}
 
 
 def workload_config(inp, args, world):
@@ -235,8 +287,7 @@ def workload_config(inp, args, world):
                         'preconditioner k=%d, tol=%g, sig=10, lam=1e-10'
                         % (args.workload, inp['kind'], inp['N'], inp['M'], inp['n'], storage, world, inp['k'], inp['tol']),
             'kernel_mode': args.mode,
-            'precon_form': (args.precon_form or 'orthonormal') +
-                           ('' if (args.no_reorth or args.precon_form == 'woodbury') else ' + complement projected twice (precon_reorth=1)'),
+            'precon_form': PRECON_FORM_TEXT[args.precon_form],
             'n': inp['n'], 'k': inp['k'],
             'tol': inp['tol'],
             'l2_policy': 'inputs larger than L2 (126 MB): every CG iteration streams this rank\'s %.1f GB of K and %.1f GB '
@@ -281,11 +332,8 @@ def run_ours(args):
     task = dict(inp['task'])
     task['kernel_mode'] = args.mode
     task['_want_hist'] = True
-    if args.precon_form:
-        task['precon_form'] = args.precon_form
-    # twice-projected complement in the preconditioner apply (DESIGN.md "Woodbury accuracy"): same operator, no
-    # residual plateau -- 900 instead of 1700 iterations on cfg2.  --no-reorth measures the plain orthonormal form.
-    task['_options'] = {} if (args.no_reorth or args.precon_form == 'woodbury') else {'precon_reorth': 1}
+    task['precon_form'] = 'orthonormal' if args.precon_form == 'reorth' else args.precon_form
+    task['_options'] = {'precon_reorth': 1} if args.precon_form == 'reorth' else {}
     task['_options'].update({kv.split('=')[0]: int(kv.split('=')[1]) for kv in args.opt})
     task['_maxiter'] = 100000   # safety net for the benchmark only (the solver's own limit is 5 n)
     dev = torch.device('cuda', local_rank)
@@ -318,24 +366,7 @@ def run_ours(args):
         out = it.solve_device(task, eng, y_t, frac, 'cholesky', n_ind)
         return it, out
 
-    # Probe solve before anything is timed: the twice-projected apply was validated on one GPU only when this
-    # was written; if it does not converge here (every rank sees the same numbers, so every rank takes the same
-    # branch) the benchmark falls back to the plain orthonormal form and says so in the JSON line.
-    reorth_fallback = None
-    probe_ok = False
-    if task['_options'].get('precon_reorth') and args.warmup > 0:   # --warmup 0 (profiling / A-B runs): no probe
-        try:
-            _, probe = one_step()
-            if probe[3] != 0:
-                reorth_fallback = 'probe solve did not converge (info = %d)' % probe[3]
-        except Exception as exc:  # noqa: BLE001
-            reorth_fallback = '%s: %s' % (type(exc).__name__, exc)
-        if reorth_fallback:
-            task['_options']['precon_reorth'] = 0
-            eng.set_option('precon_reorth', 0)
-        else:
-            probe_ok = True      # a full solve on the final path: it is the first warm-up step
-    for _ in range(max(args.warmup - (1 if probe_ok else 0), 0)):
+    for _ in range(args.warmup):
         one_step()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -468,19 +499,14 @@ def run_ours(args):
     }
     if alt is not None:
         line['alt'] = alt
-    if reorth_fallback:
-        line['config']['precon_form'] = (args.precon_form or 'orthonormal') + ' (precon_reorth fell back: %s)' % reorth_fallback
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ref_iters = int(load_constants().get(args.workload, {}).get('cg_iters_reference_form', iters))
+        ref_iters, ref_src = reference_iteration_count(args.workload, iters)
         total, detail = cpu_reference_sample(inp, ref_iters)
         line['cpu_baseline'] = {
             'value': total, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'port', 'extrapolated': True,
-            'sample': '2 full-n torch-CPU kernel matvecs, 2 Schur-update steps at m=k/2, Woodbury factor at k\'=512 '
-                      '(scaled (k/k\')^2), 3 applies at k\' (scaled k/k\'); solve = k(t_mv+t_sch)+t_fac+iters(t_mv+t_app) '
-                      'with the GPU run\'s k and the iteration count measured for the reference\'s Woodbury formula '
-                      '(bench_constants.json)',
-            'detail': detail}
+            'sample': '%s; cg_iters=%d from %s' % (CPU_SAMPLE_TEXT, ref_iters, ref_src),
+            'detail': detail, 'measured_full_solves': measured_cpu_points(args.workload)}
     if rank == 0:
         real_stdout.write(json.dumps(line) + '\n')
         real_stdout.flush()
@@ -505,9 +531,9 @@ def main():
     ap.add_argument('--no-alt', action='store_true', help='skip the extra matrix-free solve reported under "alt"')
     ap.add_argument('--tol', type=float, default=None, help='override the relative residual target (profiling runs)')
     ap.add_argument('--k', type=int, default=None, help='override the preconditioner rank')
-    ap.add_argument('--precon-form', default=None, choices=['orthonormal', 'woodbury'])
-    ap.add_argument('--no-reorth', action='store_true',
-                    help='do not project the complement twice in the preconditioner apply (library default)')
+    ap.add_argument('--precon-form', default='projected', choices=['projected', 'woodbury', 'orthonormal', 'reorth'],
+                    help="evaluation of the pivoted-Cholesky preconditioner (L L^T + lam I)^-1: 'projected' (benchmark "
+                         "default), 'woodbury' (the reference's formula, the library default), 'orthonormal', 'reorth'")
     ap.add_argument('--opt', action='append', default=[], help='library option name=int (mlffpc_set_option), repeatable')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -117,10 +117,15 @@ int mlffpc_symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full
  *   "layout_world", "layout_rank"   tile partition override (rank emulation on one GPU)
  *   "pchol_lookahead" [1]  blocked pivoted Cholesky with a candidate panel (0 = plain left-looking build)
  *   "assemble_legacy" [0]  first-generation assembly kernel (one CTA per 3N x 3N block)
- *   "precon_reorth"   [0]  EXPERIMENTAL: project the complement twice in the orthonormal-form preconditioner apply
- *                          (two more passes over the factor; removes the 1/lam leak of Qt Qt^T - I)
+ *   "gram_mode"       [1]  Gram matrices (mlffpc_syrk_rows) with (hi, lo) accumulation of the k-tile products;
+ *                          0 = one running fp64 sum per entry (the round-1 kernel: 188 instead of the reference's 119
+ *                          CG iterations on BASELINE.json configs[0])
+ *   "defect_mode"     [1]  E = Q Q^T - I of the projected form from the DMMA kernel (1) or with exact products and sums
+ *                          on the FP64 vector pipe (2, ~7x slower; the reference for the tests)
+ *   "precon_reorth"   [0]  project the complement twice in the orthonormal-form preconditioner apply (Mk given, no E):
+ *                          two more passes over the factor; the four-pass cross-check of the projected form
  *   diagnostics for the numerics study in DESIGN.md: "precon_accuracy" (1 Kahan, 2 two-halves summation of T r),
- *   "tgemv_msplit" (1/4/8), "dot_split" (1..8), "syrk_chunk" (> 0: Gram by Kahan-summed column chunks) */
+ *   "tgemv_msplit" (1/4/8), "syrk_chunk" (> 0: Gram by Kahan-summed column chunks) */
 int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value);
 
 /* Matrix-free matvec  y_local = alpha * (K v)_local + shift * v_local, v is the full n-vector.
@@ -179,29 +184,46 @@ int mlffpc_woodbury_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, d
  * operator, same traffic per apply.  W1, W2: k*k device scratch each. */
 int mlffpc_orthonormal_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, double lam, double* Mk,
                               double* W1, double* W2, void* stream);
+/* E[k,k] = Q Q^T - I for Q[k, n_cols] (this rank's columns; summed over ranks), accumulated in extended precision on
+ * the DMMA pipe: every 16-column k-tile product is folded into an unevaluated (hi, lo) sum with an error-free
+ * TwoSum (csrc/gramdd.cu), so entries of size 1e-15 come out to ~1e-18 -- a plain fp64 Gram's own rounding is as
+ * large as E.  mlffpc_syrk_rows uses the same accumulation by default (option "gram_mode" = 0 selects the single
+ * running sum of round 1). */
+int mlffpc_gram_defect(mlffpc_ctx* ctx, const double* Q, int64_t k, int64_t n_cols, int64_t ld, double* E, void* stream);
+/* mlffpc_orthonormal_factor followed by E = Qt Qt^T - I (mlffpc_gram_defect): the "projected" form.  With E the
+ * apply uses the exact projector onto range(L) to first order,
+ *     z = sign * ((r - Qt^T (w - E w)) / lam + Qt^T Mk w),   w = Qt r,
+ * in the same two passes over the factor as the reference formula.  Without E the defect of Qt Qt^T - I (~1e-15) is
+ * amplified by 1 / lam = 1e10 and splits the unit eigenvalue cluster of the preconditioned operator: the residual
+ * parks on a plateau (cfg2: 1783 iterations with the reference formula, 900 with this form). */
+int mlffpc_projected_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, double lam, double* Mk, double* E,
+                            double* W1, double* W2, void* stream);
 /* z = sign * (r - T^T (T r)) / lam  on the local rows (Mk == NULL), or with Mk from
- * mlffpc_orthonormal_factor  z = sign * ((r - T^T (T r)) / lam + T^T Mk (T r)).
- * u is a device scratch of 2 k + 4 doubles.
+ * mlffpc_orthonormal_factor  z = sign * ((r - T^T (T r)) / lam + T^T Mk (T r)), or with Mk and E from
+ * mlffpc_projected_factor the projected form above.
+ * u is a device scratch of 4 k + 8 doubles.
  * sign = +1: iterative_cholesky.py:145-148; sign = -1: the Nystroem operator
  * (iterative_solver.py:315-318) and _init_precon_operator_sb (:376-379). */
 int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
-                        const double* r, double* z, double* u, const double* Mk, void* stream);
+                        const double* r, double* z, double* u, const double* Mk, const double* E, void* stream);
 
 /* ---------------------------------------------------------------- PCG ---- */
 /* Preconditioned CG on A x = b, A = -K + lam I, with scipy-1.7.3 legacy stopping semantics
  * (||r|| <= tol ||b||, residual recomputed once on first hit; call site iterative_solver.py:995-1005).
  *   K_local: explicit local rows [n_local, n] (ld_k) or NULL for the matrix-free operator
- *   T: preconditioner factor [k, n_local] or NULL (identity); precon_sign, Mk (may be NULL) as in
+ *   T: preconditioner factor [k, n_local] or NULL (identity); precon_sign, Mk, E (may be NULL) as in
  *      mlffpc_precon_apply
  *   b, x: local rows (x in: initial guess, out: solution)
  *   out_host[8] (host doubles): iterations, final ||r||, info (0 converged), ||b||,
  *       summed operator ms, operator calls, summed preconditioner ms (CUDA events), reserved
  *   resid_hist_host: NULL or host double[maxiter+1] receiving ||r|| per iteration
+ * The stopping test runs on the device; the host reads the loop state one batch of iterations late and never waits
+ * for a scalar inside the loop (csrc/pcg.cu).  Iteration count, x and r are those of the legacy loop.
  * Workspace: mlffpc_pcg_workspace_bytes. */
 int mlffpc_pcg_workspace_bytes(mlffpc_ctx* ctx, int64_t k, int matrix_free, int64_t* bytes);
 int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam, const double* T,
-               int64_t k, int64_t ld_t, double precon_sign, const double* Mk, const double* b, double* x, double tol,
-               int64_t maxiter, double* out_host, double* resid_hist_host, void* workspace,
+               int64_t k, int64_t ld_t, double precon_sign, const double* Mk, const double* E, const double* b,
+               double* x, double tol, int64_t maxiter, double* out_host, double* resid_hist_host, void* workspace,
                int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- small vector helpers ---- */

@@ -56,9 +56,11 @@ SIGNATURES = {
     'mlffpc_pchol_build': [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     'mlffpc_woodbury_factor': [c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_ptr, c_ptr],
     'mlffpc_orthonormal_factor': [c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr],
-    'mlffpc_precon_apply': [c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    'mlffpc_gram_defect': [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr],
+    'mlffpc_projected_factor': [c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    'mlffpc_precon_apply': [c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     'mlffpc_pcg_workspace_bytes': [c_ptr, c_i64, c_int, ctypes.POINTER(c_i64)],
-    'mlffpc_pcg': [c_ptr, c_ptr, c_i64, c_dbl, c_ptr, c_i64, c_i64, c_dbl, c_ptr, c_ptr, c_ptr, c_dbl, c_i64,
+    'mlffpc_pcg': [c_ptr, c_ptr, c_i64, c_dbl, c_ptr, c_i64, c_i64, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_i64,
                    c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     'mlffpc_dot': [c_ptr, c_ptr, c_ptr, c_i64, ctypes.POINTER(c_dbl), c_ptr],
 }

@@ -97,9 +97,12 @@ struct mlffpc_ctx {
     double* reorth_scratch = nullptr;
     int64_t reorth_scratch_len = 0;
     bool assemble_legacy = false;  // option "assemble_legacy": one CTA per 3N x 3N block (the first-generation kernel)
-    int64_t syrk_chunk = 0;        // option "syrk_chunk": > 0 = Gram matrices by column chunks with Kahan-summed partials
+    int gram_mode = 1;             // option "gram_mode": 1 (default) = Gram matrices with (hi, lo) accumulation of the k-tile
+                                   // products (gramdd.cu); 0 = one running fp64 sum per entry (the round-1 kernel)
+    int defect_mode = 1;           // option "defect_mode": E = Q Q^T - I from 1 = the DMMA kernel with (hi, lo) k-tile folding,
+                                   // 2 = exact products and sums on the FP64 vector pipe (~7x slower; reference for tests)
+    int64_t syrk_chunk = 0;        // option "syrk_chunk": > 0 = Gram matrices by column chunks with Kahan-summed partials (diagnostics)
     int tgemv_msplit = 0;          // option "tgemv_msplit": force the row split of T^T u (1, 4, 8; 0 = auto)
-    int dot_split = 1;             // option "dot_split": CG dot products as the sum of this many chunk sums (diagnostics)
     int precon_accuracy = 0;       // option "precon_accuracy": 1 = Kahan-compensated T r and T^T u (diagnostics)
     bool pchol_lookahead = true;   // option "pchol_lookahead": candidate-panel (blocked) pivoted Cholesky
     long long last_pchol_refills = 0;  // panel rebuilds of the last mlffpc_pchol_build (diagnostics)
@@ -179,9 +182,13 @@ int matvec_free(mlffpc_ctx* ctx, const double* v, double* y_local, double alpha,
                 void* workspace, cudaStream_t s);
 // preconditioner apply (precon.cu)
 int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
-                 const double* r, double* z, double* u, cudaStream_t s, const double* Mk = nullptr);
+                 const double* r, double* z, double* u, cudaStream_t s, const double* Mk = nullptr,
+                 const double* E = nullptr);
 
 int ensure_reorth_scratch(mlffpc_ctx* ctx, int64_t k);
+// W = X X^T + shift I (or X X^T - I) with extended-precision accumulation, summed over ranks (gramdd.cu)
+int gram_dd(mlffpc_ctx* ctx, const double* X, int64_t m, int64_t n_cols, int64_t ldx, double* out, int64_t ld_out,
+            double shift, bool minus_identity, cudaStream_t s, bool exact = false);
 // internal dense building blocks (dense.cu), all on `s`
 // nsplit > 1: split-K, slice z writes its partial product to C + z * c_zstride (beta applies to every slice)
 int dgemm(bool transB, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,

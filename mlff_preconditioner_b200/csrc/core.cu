@@ -141,7 +141,7 @@ using namespace mlffpc;
 
 extern "C" {
 
-int mlffpc_version(void) { return 100; }
+int mlffpc_version(void) { return 200; }
 
 int64_t mlffpc_launch_count(void) { return (int64_t)g_launches; }
 
@@ -221,8 +221,9 @@ int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value) {
         return MLFFPC_OK;
     }
     if (nm == "assemble_legacy") { ctx->assemble_legacy = value != 0; return MLFFPC_OK; }
+    if (nm == "defect_mode") { ctx->defect_mode = value == 2 ? 2 : 1; return MLFFPC_OK; }
+    if (nm == "gram_mode") { ctx->gram_mode = value != 0 ? 1 : 0; return MLFFPC_OK; }
     if (nm == "syrk_chunk") { ctx->syrk_chunk = value > 0 ? value : 0; return MLFFPC_OK; }
-    if (nm == "dot_split") { ctx->dot_split = value >= 1 && value <= 8 ? (int)value : 1; return MLFFPC_OK; }
     if (nm == "precon_accuracy") { ctx->precon_accuracy = (int)value; return MLFFPC_OK; }
     if (nm == "pchol_lookahead") { ctx->pchol_lookahead = value != 0; return MLFFPC_OK; }
     if (nm == "layout_world") {

@@ -350,6 +350,13 @@ int mlffpc_syrk_rows(mlffpc_ctx* ctx, const double* X, int64_t m, int64_t n_cols
     pw.step(pw.first);
     int st_gemm = MLFFPC_OK;
     const int64_t chunk = ctx->syrk_chunk;
+    if (ctx->gram_mode == 1 && chunk <= 0) {
+        // default: k-tile products folded into an unevaluated (hi, lo) sum on the DMMA pipe (gramdd.cu); includes the
+        // cross-rank reduction, the mirror to the upper triangle and the diagonal shift
+        st_gemm = gram_dd(ctx, X, m, n_cols, ldx, W, ldw, shift, false, s);
+        pw.end();
+        return st_gemm;
+    }
     if (chunk > 0 && n_cols > chunk) {
         // The Gram of 1e5-long rows loses ~sqrt(n) eps relative accuracy in a single running sum; against
         // lam = 1e-10 that is a visible perturbation of the Woodbury inverse ("Woodbury accuracy").

@@ -1,8 +1,22 @@
-// Preconditioned CG driver with device-resident scalars and fused vector kernels.
+// Preconditioned CG driver: device-resident scalars, fused vector kernels, convergence decided on the device.
+//
 // Recurrence and stopping rule restate scipy 1.7.3 sparse.linalg.cg(tol=, atol=None) as called by the
 // reference (solvers/iterative_solver.py:995-1005): atol = tol*||b||, probe ||A x0 - b|| <= tol first,
 // on the first ||r|| <= atol after iteration 1 recompute r = b - A x once and re-test.
+//
+// The host never waits for a scalar inside the loop.  Iterations are launched in short batches; the kernels
+// that change x, r, p or the scalars return at once when the device-side state says "frozen", which the first
+// kernel to see ||r||^2 <= atol^2 sets together with the iteration number.  The host reads the 32-byte state one
+// batch late (pinned memory, an event per batch), so the GPU never idles on it; the iterations launched past the
+// stopping point are no-ops for the state (their operator / preconditioner kernels still run, a few milliseconds).
+// ||r||^2 of iteration j travels with rho of iteration j + 1 in ONE two-element allreduce, so a sharded run
+// issues two scalar collectives per iteration instead of three; the test of iteration j therefore happens in the
+// p-update kernel of iteration j + 1, before anything is modified -- x, r, p and the iteration count are
+// exactly those of the legacy loop.
 #include <math.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -11,11 +25,22 @@ namespace mlffpc {
 constexpr int VEC_THREADS = 256;
 constexpr int VEC_MAX_BLOCKS = 1024;
 
-// scalar slots in ctx->scal
-enum { S_RHO0 = 0, S_RHO1 = 1, S_PQ = 2, S_RR = 3, S_TMP = 4, S_COUNTER = 8 /* unsigned */ };
+// scalar slots in ctx->scal used by mlffpc_dot
+enum { S_TMP = 4, S_COUNTER = 8 /* unsigned */ };
+
+// device-side loop state (in the workspace; mirrored to pinned host memory once per batch)
+struct PcgState {
+    int frozen;        // 1: the stopping test fired (or NaN) -- vector kernels are no-ops until the host clears it
+    int conv_iter;     // iteration whose residual passed the test
+    int nan_flag;      // residual became NaN at conv_iter
+    int last_iter;     // last iteration whose ||r||^2 has been recorded
+    double last_rr;    // ||r||^2 of last_iter (global)
+    double pad;
+};
+// red[0] = rho (r.z), red[1] = ||r||^2 of the previous update, red[2] = p.q, red[3] = rho of the previous iteration
 
 // deterministic grid reduction: per-block partials, the last block to finish sums them in index order
-__device__ __forceinline__ void grid_reduce_store(double v, double* partials, unsigned* counter, double* out) {
+__device__ __forceinline__ bool grid_reduce(double v, double* partials, unsigned* counter, double* result) {
     __shared__ double sm[40];
     __shared__ bool is_last;
     v = block_sum(v, sm);
@@ -26,39 +51,62 @@ __device__ __forceinline__ void grid_reduce_store(double v, double* partials, un
         is_last = (done == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last) {
-        __threadfence();
-        double t = 0.0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += ((volatile double*)partials)[i];
-        t = block_sum(t, sm);
-        if (threadIdx.x == 0) {
-            *out = t;
-            *counter = 0u;
-        }
+    if (!is_last) return false;
+    __threadfence();
+    double t = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += ((volatile double*)partials)[i];
+    t = block_sum(t, sm);
+    if (threadIdx.x == 0) {
+        *result = t;
+        *counter = 0u;
     }
+    return threadIdx.x == 0;
 }
 
+// out = sum a[i] b[i]  (state == NULL: unconditional; otherwise the store is skipped while frozen)
 __global__ void dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
-                           double* partials, unsigned* counter, double* out) {
+                           double* partials, unsigned* counter, double* out, const PcgState* state) {
+    if (state && state->frozen) return;
     double v = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         v = fma(a[i], b[i], v);
-    grid_reduce_store(v, partials, counter, out);
+    __shared__ double res;
+    if (grid_reduce(v, partials, counter, &res)) *out = res;
 }
 
-// p = z + (rho/rho_prev) p   (first = 1: p = z)
-__global__ void update_p_kernel(const double* __restrict__ z, double* __restrict__ p, int64_t n,
-                                const double* __restrict__ rho, const double* __restrict__ rho_prev, int first) {
-    const double beta = first ? 0.0 : (*rho / *rho_prev);
+// Stopping test of iteration it - 1 (its ||r||^2 = red[1], global after the allreduce) and, unless it fires,
+// p = z + (rho / rho_prev) p  (it == 1: p = z).  only_check = 1: the test alone (after the last iteration).
+__global__ void update_p_kernel(const double* __restrict__ z, double* __restrict__ p, int64_t n, const double* red,
+                                const double* red_test, PcgState* state, double atol2, int64_t it, int only_check,
+                                double* __restrict__ hist) {
+    const bool was_frozen = state->frozen != 0;
+    const double rr = red_test[1];
+    const bool test = it > 1;  // nothing to test before the first update
+    const bool fire = test && (!(rr == rr) || rr <= atol2);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !was_frozen && test) {
+        state->last_iter = (int)(it - 1);
+        state->last_rr = rr;
+        if (hist) hist[it - 1] = rr;
+        if (fire) {
+            state->conv_iter = (int)(it - 1);
+            state->nan_flag = (rr == rr) ? 0 : 1;
+            __threadfence();
+            state->frozen = 1;
+        }
+    }
+    if (was_frozen || fire || only_check) return;
+    const double beta = (it == 1) ? 0.0 : (red[0] / red[3]);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        p[i] = first ? z[i] : fma(beta, p[i], z[i]);
+        p[i] = (it == 1) ? z[i] : fma(beta, p[i], z[i]);
 }
 
-// alpha = rho/pq; x += alpha p; r -= alpha q; rr = sum r^2
+// alpha = rho / (p.q); x += alpha p; r -= alpha q; red[1] = sum r^2 (local); red[3] = rho
 __global__ void update_xr_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
-                                 const double* __restrict__ q, int64_t n, const double* __restrict__ rho,
-                                 const double* __restrict__ pq, double* partials, unsigned* counter, double* rr) {
-    const double alpha = *rho / *pq;
+                                 const double* __restrict__ q, int64_t n, double* red, const PcgState* state,
+                                 double* partials, unsigned* counter) {
+    if (state->frozen) return;
+    const double rho = red[0];
+    const double alpha = rho / red[2];
     double v = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         x[i] = fma(alpha, p[i], x[i]);
@@ -66,10 +114,14 @@ __global__ void update_xr_kernel(double* __restrict__ x, double* __restrict__ r,
         r[i] = ri;
         v = fma(ri, ri, v);
     }
-    grid_reduce_store(v, partials, counter, rr);
+    __shared__ double res;
+    if (grid_reduce(v, partials, counter, &res)) {
+        red[1] = res;
+        red[3] = rho;
+    }
 }
 
-// r = b - q ; rr = sum r^2
+// r = b - q ; *rr = sum r^2 (local)
 __global__ void residual_kernel(const double* __restrict__ b, const double* __restrict__ q, double* __restrict__ r,
                                 int64_t n, double* partials, unsigned* counter, double* rr) {
     double v = 0.0;
@@ -78,15 +130,8 @@ __global__ void residual_kernel(const double* __restrict__ b, const double* __re
         r[i] = ri;
         v = fma(ri, ri, v);
     }
-    grid_reduce_store(v, partials, counter, rr);
-}
-
-__global__ void sum_slots_kernel(double* out, const double* parts, int count) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double t = 0.0;
-        for (int i = 0; i < count; ++i) t += parts[i];
-        *out = t;
-    }
+    __shared__ double res;
+    if (grid_reduce(v, partials, counter, &res)) *rr = res;
 }
 
 static inline unsigned vec_grid(int64_t n) {
@@ -97,8 +142,9 @@ static inline unsigned vec_grid(int64_t n) {
 }
 
 struct PcgWs {
-    int64_t n_pad, off_r, off_z, off_q, off_p, off_xg, off_u, off_mv, off_symv, total;
+    int64_t n_pad, off_r, off_z, off_q, off_p, off_xg, off_u, off_mv, off_symv, off_state, off_hist, hist_len, total;
 };
+constexpr int64_t PCG_HIST_CAP = 1 << 20;  // device-side ||r||^2 history entries (longer runs keep the first 2^20)
 static PcgWs pcg_layout(const mlffpc_ctx* c, int64_t k, bool matrix_free) {
     auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
     PcgWs w;
@@ -112,9 +158,12 @@ static PcgWs pcg_layout(const mlffpc_ctx* c, int64_t k, bool matrix_free) {
     w.off_q = o; o = up(o + nl * 8);
     w.off_p = o; o = up(o + world * w.n_pad * 8);
     w.off_xg = o; o = up(o + (world > 1 ? world * w.n_pad * 8 : 0));
-    w.off_u = o; o = up(o + (2 * k + 4) * 8);
+    w.off_u = o; o = up(o + (4 * k + 8) * 8);
     w.off_mv = o; o = up(o + (matrix_free ? matvec_free_ws_bytes(c) : 0));
     w.off_symv = o; o = up(o + ((!matrix_free && c->use_symv) ? symop_ws_bytes(c) : 0));
+    w.off_state = o; o = up(o + 256);  // PcgState + red[8]
+    w.hist_len = PCG_HIST_CAP;
+    w.off_hist = o; o = up(o + w.hist_len * 8);
     w.total = o + 256;
     return w;
 }
@@ -136,6 +185,28 @@ struct PcgOp {
     }
 };
 
+// events of the loop, destroyed on every exit path
+struct EventRing {
+    std::vector<cudaEvent_t> ev;
+    ~EventRing() {
+        for (auto e : ev) cudaEventDestroy(e);
+    }
+    int init(size_t count) {
+        ev.reserve(count);
+        for (size_t i = 0; i < count; ++i) {
+            cudaEvent_t e;
+            cudaError_t err = cudaEventCreate(&e);
+            if (err != cudaSuccess) return cuda_fail(err, "cudaEventCreate", __FILE__, __LINE__);
+            ev.push_back(e);
+        }
+        return MLFFPC_OK;
+    }
+};
+struct ProfGuard {
+    ProfWindow pw;
+    ~ProfGuard() { pw.end(); }
+};
+
 }  // namespace mlffpc
 
 using namespace mlffpc;
@@ -146,7 +217,7 @@ int mlffpc_dot(mlffpc_ctx* ctx, const double* a, const double* b, int64_t n, dou
     MLFFPC_REQUIRE(ctx && a && b && out_host && n >= 0, "dot: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
     unsigned* counter = (unsigned*)(ctx->scal + S_COUNTER);
-    dot_kernel<<<vec_grid(n), VEC_THREADS, 0, s>>>(a, b, n, ctx->partials, counter, ctx->scal + S_TMP);
+    dot_kernel<<<vec_grid(n), VEC_THREADS, 0, s>>>(a, b, n, ctx->partials, counter, ctx->scal + S_TMP, nullptr);
     MLFFPC_LAUNCH_CHECK();
     MLFFPC_TRY(comm_allreduce_sum(ctx->comm, ctx->scal + S_TMP, 1, s));
     MLFFPC_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->scal + S_TMP, 8, cudaMemcpyDeviceToHost, s));
@@ -162,15 +233,17 @@ int mlffpc_pcg_workspace_bytes(mlffpc_ctx* ctx, int64_t k, int matrix_free, int6
 }
 
 int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam, const double* T,
-               int64_t k, int64_t ld_t, double precon_sign, const double* Mk, const double* b, double* x, double tol,
-               int64_t maxiter, double* out_host, double* resid_hist_host, void* workspace,
+               int64_t k, int64_t ld_t, double precon_sign, const double* Mk, const double* E, const double* b,
+               double* x, double tol, int64_t maxiter, double* out_host, double* resid_hist_host, void* workspace,
                int64_t workspace_bytes, void* stream) {
     MLFFPC_REQUIRE(ctx && ctx->M > 0, "pcg: geometry not set");
     MLFFPC_REQUIRE(b && x && out_host && workspace, "pcg: NULL argument");
     MLFFPC_REQUIRE(lam > 0.0 && tol > 0.0 && maxiter >= 0, "pcg: bad lam/tol/maxiter");
+    MLFFPC_REQUIRE(maxiter < ((int64_t)1 << 31) - 8, "pcg: maxiter too large");
     MLFFPC_REQUIRE(!K_local || ctx->use_symv || ld_k >= ctx->n, "pcg: ld_k < n");
     MLFFPC_REQUIRE(!ctx->use_symv || ctx->lay_world == ctx->comm.world, "pcg: symmetric tile layout does not match the communicator");
     MLFFPC_REQUIRE(!T || (k > 0 && ld_t >= ctx->n_local()), "pcg: bad preconditioner dimensions");
+    MLFFPC_REQUIRE(!E || Mk, "pcg: the defect matrix E needs the orthonormal-form Mk");
     const bool matrix_free = (K_local == nullptr);
     if (T && Mk) MLFFPC_TRY(ensure_reorth_scratch(ctx, k));
     const PcgWs w = pcg_layout(ctx, T ? k : 0, matrix_free);
@@ -191,36 +264,21 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     double* p = p_full + row0;
     double* xg = (world > 1) ? (double*)(base + w.off_xg) : nullptr;
     double* u = (double*)(base + w.off_u);
+    PcgState* state = (PcgState*)(base + w.off_state);
+    double* red = (double*)(base + w.off_state + 64);
+    double* hist = (double*)(base + w.off_hist);
     PcgOp A{ctx, K_local, ld_k, lam, (void*)(base + w.off_mv), (void*)(base + w.off_symv)};
     double* sc = ctx->scal;
     unsigned* counter = (unsigned*)(sc + S_COUNTER);
     const unsigned g = vec_grid(nl);
 
-    // dot(a, b) -> *out; with dot_split > 1 the sum is formed chunk by chunk like a multi-rank run would (diagnostics)
-    const int dsplit = ctx->dot_split;
-    auto dot_to = [&](const double* a, const double* bvec, double* out) -> int {
-        if (dsplit <= 1) {
-            dot_kernel<<<g, VEC_THREADS, 0, s>>>(a, bvec, nl, ctx->partials, counter, out);
-            MLFFPC_LAUNCH_CHECK();
-            return MLFFPC_OK;
-        }
-        const int64_t chunk = (nl + dsplit - 1) / dsplit;
-        for (int c = 0; c < dsplit; ++c) {
-            const int64_t o = c * chunk, len = (o + chunk <= nl) ? chunk : (nl - o > 0 ? nl - o : 0);
-            dot_kernel<<<vec_grid(len), VEC_THREADS, 0, s>>>(a + o, bvec + o, len, ctx->partials, counter, sc + 16 + c);
-            MLFFPC_LAUNCH_CHECK();
-        }
-        sum_slots_kernel<<<1, 32, 0, s>>>(out, sc + 16, dsplit);
-        MLFFPC_LAUNCH_CHECK();
-        return MLFFPC_OK;
-    };
-    auto host_scalar = [&](int slot, double* out) -> int {
-        MLFFPC_CUDA(cudaMemcpyAsync(ctx->h_scal, sc + slot, 8, cudaMemcpyDeviceToHost, s));
+    auto host_scalar = [&](const double* dev, double* out) -> int {
+        MLFFPC_CUDA(cudaMemcpyAsync(ctx->h_scal, dev, 8, cudaMemcpyDeviceToHost, s));
         MLFFPC_CUDA(cudaStreamSynchronize(s));
         *out = ctx->h_scal[0];
         return MLFFPC_OK;
     };
-    // q = A x (x gathered when sharded), r = b - q, rr -> S_RR
+    // q = A x (x gathered when sharded), r = b - q, local ||r||^2 -> red[1]
     auto true_residual = [&]() -> int {
         const double* x_full = x;
         if (world > 1) {
@@ -230,92 +288,179 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
             x_full = xg;
         }
         MLFFPC_TRY(A.apply(x_full, q, s));
-        residual_kernel<<<g, VEC_THREADS, 0, s>>>(b, q, r, nl, ctx->partials, counter, sc + S_RR);
+        residual_kernel<<<g, VEC_THREADS, 0, s>>>(b, q, r, nl, ctx->partials, counter, red + 1);
         MLFFPC_LAUNCH_CHECK();
-        return comm_allreduce_sum(ctx->comm, sc + S_RR, 1, s);
+        return MLFFPC_OK;
+    };
+    // global ||r|| from the local red[1] without disturbing it (the loop's allreduce expects the local value)
+    auto global_resid = [&](double* out) -> int {
+        MLFFPC_CUDA(cudaMemcpyAsync(sc + S_TMP, red + 1, 8, cudaMemcpyDeviceToDevice, s));
+        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, sc + S_TMP, 1, s));
+        double rr = 0.0;
+        MLFFPC_TRY(host_scalar(sc + S_TMP, &rr));
+        *out = sqrt(rr);
+        return MLFFPC_OK;
     };
 
-    double bb = 0.0, rr = 0.0;
-    dot_kernel<<<g, VEC_THREADS, 0, s>>>(b, b, nl, ctx->partials, counter, sc + S_TMP);
+    MLFFPC_CUDA(cudaMemsetAsync(base + w.off_state, 0, 256, s));
+    double bb = 0.0;
+    dot_kernel<<<g, VEC_THREADS, 0, s>>>(b, b, nl, ctx->partials, counter, sc + S_TMP, nullptr);
     MLFFPC_LAUNCH_CHECK();
     MLFFPC_TRY(comm_allreduce_sum(ctx->comm, sc + S_TMP, 1, s));
-    MLFFPC_TRY(host_scalar(S_TMP, &bb));
+    MLFFPC_TRY(host_scalar(sc + S_TMP, &bb));
     const double bnrm2 = sqrt(bb);
 
+    double resid = 0.0;
     MLFFPC_TRY(true_residual());
-    MLFFPC_TRY(host_scalar(S_RR, &rr));
-    double resid = sqrt(rr);
+    MLFFPC_TRY(global_resid(&resid));
     out_host[3] = bnrm2;
+    out_host[4] = out_host[5] = out_host[6] = out_host[7] = 0.0;
     if (resid_hist_host) resid_hist_host[0] = resid;
     if (resid <= tol) {  // legacy _get_atol probe
         out_host[0] = 0; out_host[1] = resid; out_host[2] = 0;
-        out_host[4] = out_host[5] = out_host[6] = 0;
         return MLFFPC_OK;
     }
     const double atol = (bnrm2 == 0.0) ? tol : tol * bnrm2;
+    const double atol2 = atol * atol;
     if (world > 1) MLFFPC_CUDA(cudaMemsetAsync(p_full, 0, (size_t)world * w.n_pad * 8, s));
 
-    // per-iteration CUDA-event timing of the operator and the preconditioner (the host syncs once per
-    // iteration anyway, so reading the events costs nothing extra)
-    cudaEvent_t ev[4];
-    for (auto& e : ev) MLFFPC_CUDA(cudaEventCreate(&e));
+    // batches of iterations; the state of batch i is read while batch i + 1 runs
+    constexpr int BATCH = 4, SLOTS = 2;
+    PcgState* h_state = (PcgState*)(ctx->h_scal + 16);  // pinned, SLOTS entries of 32 bytes
+    EventRing ring;                                     // per slot: BATCH * 4 timing events + 1 "state copied" event
+    MLFFPC_TRY(ring.init((size_t)SLOTS * (BATCH * 4 + 1)));
+    auto ev_iter = [&](int slot, int i, int which) { return ring.ev[(size_t)slot * (BATCH * 4 + 1) + i * 4 + which]; };
+    auto ev_done = [&](int slot) { return ring.ev[(size_t)slot * (BATCH * 4 + 1) + BATCH * 4]; };
     double op_ms = 0.0, pre_ms = 0.0;
     int64_t op_calls = 0;
+    int slot_iters[SLOTS] = {0, 0};
+    auto harvest = [&](int slot) -> int {  // wait for the slot's batch, add up its event times
+        if (slot_iters[slot] == 0) return MLFFPC_OK;
+        MLFFPC_CUDA(cudaEventSynchronize(ev_done(slot)));
+        for (int i = 0; i < slot_iters[slot]; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev_iter(slot, i, 0), ev_iter(slot, i, 1)) == cudaSuccess) pre_ms += ms;
+            if (cudaEventElapsedTime(&ms, ev_iter(slot, i, 2), ev_iter(slot, i, 3)) == cudaSuccess) { op_ms += ms; ++op_calls; }
+        }
+        slot_iters[slot] = 0;
+        return MLFFPC_OK;
+    };
 
-    int64_t it = 0;
-    int info = (int)(maxiter > 0x7fffffff ? 0x7fffffff : maxiter);
-    if (info == 0) info = 1;
-    ProfWindow pw = prof_window("pcg");
-    while (it < maxiter) {
-        ++it;
-        pw.step(it);
-        double* rho = sc + (it & 1);
-        double* rho_prev = sc + ((it - 1) & 1);
-        // z = P r
-        cudaEventRecord(ev[0], s);
+    // one iteration, launched without waiting for anything
+    auto launch_iteration = [&](int64_t it, int slot, int i) -> int {
+        MLFFPC_CUDA(cudaEventRecord(ev_iter(slot, i, 0), s));
         if (T) {
-            MLFFPC_TRY(precon_apply(ctx, T, k, ld_t, lam, precon_sign, r, z, u, s, Mk));
+            MLFFPC_TRY(precon_apply(ctx, T, k, ld_t, lam, precon_sign, r, z, u, s, Mk, E));
         } else {
             MLFFPC_CUDA(cudaMemcpyAsync(z, r, nl * 8, cudaMemcpyDeviceToDevice, s));
         }
-        cudaEventRecord(ev[1], s);
-        MLFFPC_TRY(dot_to(r, z, rho));
-        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, rho, 1, s));
-        update_p_kernel<<<g, VEC_THREADS, 0, s>>>(z, p, nl, rho, rho_prev, it == 1 ? 1 : 0);
+        MLFFPC_CUDA(cudaEventRecord(ev_iter(slot, i, 1), s));
+        dot_kernel<<<g, VEC_THREADS, 0, s>>>(r, z, nl, ctx->partials, counter, red + 0, state);
+        MLFFPC_LAUNCH_CHECK();
+        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, red, 2, s));  // (rho, ||r||^2 of the previous update)
+        update_p_kernel<<<g, VEC_THREADS, 0, s>>>(z, p, nl, red, red, state, atol2, it, 0, it - 1 < w.hist_len ? hist : nullptr);
         MLFFPC_LAUNCH_CHECK();
         if (world > 1) MLFFPC_TRY(comm_allgather(ctx->comm, p, p_full, w.n_pad * 8, s));
-        cudaEventRecord(ev[2], s);
+        MLFFPC_CUDA(cudaEventRecord(ev_iter(slot, i, 2), s));
         MLFFPC_TRY(A.apply(p_full, q, s));
-        cudaEventRecord(ev[3], s);
-        MLFFPC_TRY(dot_to(p, q, sc + S_PQ));
-        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, sc + S_PQ, 1, s));
-        update_xr_kernel<<<g, VEC_THREADS, 0, s>>>(x, r, p, q, nl, rho, sc + S_PQ, ctx->partials, counter, sc + S_RR);
+        MLFFPC_CUDA(cudaEventRecord(ev_iter(slot, i, 3), s));
+        dot_kernel<<<g, VEC_THREADS, 0, s>>>(p, q, nl, ctx->partials, counter, red + 2, state);
         MLFFPC_LAUNCH_CHECK();
-        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, sc + S_RR, 1, s));
-        MLFFPC_TRY(host_scalar(S_RR, &rr));
-        {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) pre_ms += ms;
-            if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) { op_ms += ms; ++op_calls; }
+        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, red + 2, 1, s));
+        update_xr_kernel<<<g, VEC_THREADS, 0, s>>>(x, r, p, q, nl, red, state, ctx->partials, counter);
+        MLFFPC_LAUNCH_CHECK();
+        return MLFFPC_OK;
+    };
+    // the stopping test of the last launched iteration (its ||r||^2 is still local in red[1])
+    // (on a copy: the next iteration's allreduce expects the local value in red[1])
+    auto launch_check = [&](int64_t it_next) -> int {
+        MLFFPC_CUDA(cudaMemcpyAsync(red + 4, red, 16, cudaMemcpyDeviceToDevice, s));
+        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, red + 4, 2, s));
+        update_p_kernel<<<1, 32, 0, s>>>(z, p, nl, red, red + 4, state, atol2, it_next, 1, it_next - 1 < w.hist_len ? hist : nullptr);
+        MLFFPC_LAUNCH_CHECK();
+        return MLFFPC_OK;
+    };
+
+    if (maxiter == 0) {
+        out_host[0] = 0; out_host[1] = resid; out_host[2] = 1;
+        return MLFFPC_OK;
+    }
+    ProfGuard prof{prof_window("pcg")};
+    int64_t launched = 0;      // iterations launched so far
+    int64_t it = 0;            // result: iterations the legacy loop would have run
+    int info = (int)(maxiter > 0x7fffffff ? 0x7fffffff : maxiter);
+    if (info == 0) info = 1;
+    bool done = false;
+    int slot = 0;
+    double known_rr = resid * resid;  // latest ||r||^2 the host has seen (lags by up to two batches)
+    while (!done) {
+        // near the target (or in a profiling window) go one iteration at a time so that nothing runs past the stop
+        const bool careful = known_rr <= 4.0 * atol2 || prof.pw.first >= 0;
+        const int nb = (int)std::min<int64_t>(careful ? 1 : BATCH, maxiter - launched);
+        MLFFPC_TRY(harvest(slot));  // the slot's events and host copy are about to be reused
+        for (int i = 0; i < nb; ++i) {
+            prof.pw.step(launched + 1);
+            MLFFPC_TRY(launch_iteration(launched + 1, slot, i));
+            ++launched;
         }
-        resid = sqrt(rr);
-        if (!(resid == resid)) {  // NaN: breakdown
+        if (launched == maxiter || careful) MLFFPC_TRY(launch_check(launched + 1));
+        slot_iters[slot] = nb;
+        MLFFPC_CUDA(cudaMemcpyAsync(&h_state[slot], state, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
+        MLFFPC_CUDA(cudaEventRecord(ev_done(slot), s));
+        // look at the batch before this one (already finished or about to), or at this one when it was the last
+        const bool last = (launched == maxiter) || careful;
+        const int look = last ? slot : (slot ^ 1);
+        if (last) MLFFPC_TRY(harvest(slot ^ 1));
+        const bool have = slot_iters[look] > 0;
+        if (have) MLFFPC_TRY(harvest(look));
+        slot ^= 1;
+        if (!have) continue;
+        const PcgState hs = h_state[look];
+        if (hs.last_iter > 0) known_rr = hs.last_rr;
+        if (!hs.frozen) {
+            if (launched == maxiter && last) { it = maxiter; resid = sqrt(known_rr); done = true; }
+            continue;
+        }
+        // the test fired at iteration hs.conv_iter; everything launched after it left x, r, p untouched
+        MLFFPC_TRY(harvest(0));
+        MLFFPC_TRY(harvest(1));
+        MLFFPC_CUDA(cudaStreamSynchronize(s));
+        it = hs.conv_iter;
+        if (hs.nan_flag) {
             set_error("pcg: residual became NaN at iteration %lld", (long long)it);
             return MLFFPC_ERR_LINALG;
         }
-        if (resid <= atol && it > 1) {
+        resid = sqrt(hs.last_rr);
+        if (it > 1) {  // legacy: recompute r = b - A x once on the first hit and test again
             MLFFPC_TRY(true_residual());
-            MLFFPC_TRY(host_scalar(S_RR, &rr));
-            resid = sqrt(rr);
+            MLFFPC_TRY(global_resid(&resid));
+            if (it < w.hist_len) {
+                const double rr_true = resid * resid;
+                MLFFPC_CUDA(cudaMemcpyAsync(hist + it, &rr_true, 8, cudaMemcpyHostToDevice, s));
+                MLFFPC_CUDA(cudaStreamSynchronize(s));
+            }
         }
-        if (resid_hist_host) resid_hist_host[it] = resid;
         if (resid <= atol) {
             info = 0;
-            break;
+            done = true;
+        } else if (it >= maxiter) {
+            done = true;
+        } else {
+            // not converged after all: continue from iteration it + 1 with the recomputed residual
+            MLFFPC_CUDA(cudaMemsetAsync(state, 0, sizeof(PcgState), s));
+            launched = it;
+            known_rr = resid * resid;
         }
     }
-    pw.end();
-    for (auto& e : ev) cudaEventDestroy(e);
+    if (resid_hist_host) {
+        const int64_t cnt = std::min<int64_t>(it, w.hist_len - 1);
+        if (cnt > 0) {
+            MLFFPC_CUDA(cudaMemcpyAsync(resid_hist_host + 1, hist + 1, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s));
+            MLFFPC_CUDA(cudaStreamSynchronize(s));
+            for (int64_t i = 1; i <= cnt; ++i) resid_hist_host[i] = sqrt(resid_hist_host[i]);
+        }
+        if (it <= cnt) resid_hist_host[it] = resid;
+    }
     out_host[0] = (double)it;
     out_host[1] = resid;
     out_host[2] = (double)info;

@@ -25,12 +25,28 @@ int ensure_reorth_scratch(mlffpc_ctx* ctx, int64_t k) {
     return MLFFPC_OK;
 }
 
-// u: device scratch of 2 k + 4 doubles.  Mk == NULL: Woodbury form z = sign (r - T^T T r) / lam.
+// u: device scratch of 4 k + 8 doubles.  Mk == NULL: Woodbury form z = sign (r - T^T T r) / lam.
 // Mk != NULL: T holds an orthonormal basis Q^T of range(L) and Mk = (Q^T L L^T Q + lam I)^{-1}:
 //   z = sign ( (r - Q (Q^T r)) / lam + Q Mk (Q^T r) ).
 int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
-                 const double* r, double* z, double* u, cudaStream_t s, const double* Mk) {
+                 const double* r, double* z, double* u, cudaStream_t s, const double* Mk, const double* E) {
     const int64_t nl = ctx->n_local();
+    if (Mk && E) {
+        // Projected form, two passes over the factor.  T = Qt has orthonormal rows up to the defect
+        // E = Qt Qt^T - I (~1e-15), which the complement term (r - Qt^T Qt r) / lam would amplify by 1 / lam = 1e10.
+        // With w = Qt r the exact projector onto range(Qt^T) is Qt^T (I + E)^{-1} Qt = Qt^T (I - E) Qt + O(E^2):
+        //   z = sign ( (r - Qt^T (w - E w)) / lam + Qt^T Mk w ).
+        // E comes from the extended-precision Gram of gramdd.cu; both k x k products are replicated on every rank.
+        const int64_t ko = (k + 3) & ~(int64_t)1;
+        double* w = u;
+        double* g1 = u + ko;       // w - E w
+        double* g2 = u + 2 * ko;   // Mk w
+        MLFFPC_TRY(launch_gemv_rows(T, k, nl, ld, r, w, 1.0, 0.0, 0, s, false));
+        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, w, (size_t)k, s));
+        MLFFPC_TRY(launch_gemv_rows(E, k, k, k, w, g1, -1.0, 1.0, 0, s, false));
+        MLFFPC_TRY(launch_gemv_rows(Mk, k, k, k, w, g2, 1.0, 0.0, 0, s, false));
+        return launch_tgemv_cols(T, k, nl, ld, g1, z, 1, r, sign / lam, ctx->num_sms, s, false, ctx->tgemv_msplit, g2, sign);
+    }
     // u = T r  (local part), summed over ranks
     const bool comp = ctx->precon_accuracy == 1;
     if (ctx->precon_accuracy == 2 && nl >= 4) {
@@ -173,10 +189,22 @@ int mlffpc_orthonormal_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld
     return MLFFPC_OK;
 }
 
+int mlffpc_projected_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, double lam, double* Mk, double* E,
+                            double* W1, double* W2, void* stream) {
+    MLFFPC_REQUIRE(E != nullptr, "projected_factor: E is NULL");
+    MLFFPC_TRY(mlffpc_orthonormal_factor(ctx, Lt, k, ld, lam, Mk, W1, W2, stream));
+    ProfWindow pw = prof_window("woodbury");
+    pw.step(pw.first);
+    const int st = gram_dd(ctx, Lt, k, ctx->n_local(), ld, E, k, 0.0, true, (cudaStream_t)stream, ctx->defect_mode == 2);
+    pw.end();
+    return st;
+}
+
 int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double lam, double sign,
-                        const double* r, double* z, double* u, const double* Mk, void* stream) {
+                        const double* r, double* z, double* u, const double* Mk, const double* E, void* stream) {
     MLFFPC_REQUIRE(ctx && ctx->M > 0, "precon_apply: geometry not set");
     MLFFPC_REQUIRE(r && z && lam > 0.0, "precon_apply: bad argument");
+    MLFFPC_REQUIRE(!E || Mk, "precon_apply: the defect matrix E needs the orthonormal-form Mk");
     cudaStream_t s = (cudaStream_t)stream;
     if (k == 0 || T == nullptr) {
         const int64_t nl = ctx->n_local();
@@ -186,7 +214,7 @@ int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld,
     }
     MLFFPC_REQUIRE(u && ld >= ctx->n_local(), "precon_apply: bad argument");
     if (Mk) MLFFPC_TRY(ensure_reorth_scratch(ctx, k));
-    return precon_apply(ctx, T, k, ld, lam, sign, r, z, u, s, Mk);
+    return precon_apply(ctx, T, k, ld, lam, sign, r, z, u, s, Mk, E);
 }
 
 }  // extern "C"

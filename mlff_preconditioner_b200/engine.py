@@ -339,17 +339,35 @@ class Engine(object):
                                                       _ptr(W1), _ptr(W2), self._stream()))
         return Lt, Mk
 
-    def precon_apply(self, T, lam, sign, r, out=None, Mk=None):
+    def projected_factor_(self, Lt, lam):
+        """In place: Lt -> Qt as in ``orthonormal_factor_``; returns (Qt, Mk, E) with the defect
+        E = Qt Qt^T - I from the extended-precision Gram (csrc/gramdd.cu) -- the two-pass projected form."""
+        k = Lt.shape[0]
+        Mk, E, W1, W2 = self.empty(k, k), self.empty(k, k), self.empty(k, k), self.empty(k, k)
+        _lib.check(self.lib.mlffpc_projected_factor(self.ctx, _ptr(Lt), k, Lt.stride(0), float(lam), _ptr(Mk), _ptr(E),
+                                                    _ptr(W1), _ptr(W2), self._stream()))
+        return Lt, Mk, E
+
+    def gram_defect(self, Q):
+        """E = Q Q^T - I for Q[k, n_local] (summed over ranks), extended-precision accumulation."""
+        k = Q.shape[0]
+        E = self.empty(k, k)
+        _lib.check(self.lib.mlffpc_gram_defect(self.ctx, _ptr(Q), k, Q.shape[1], Q.stride(0), _ptr(E), self._stream()))
+        return E
+
+    def precon_apply(self, T, lam, sign, r, out=None, Mk=None, E=None):
         if out is None:
             out = self.empty(self.n_local)
         k = 0 if T is None else T.shape[0]
-        u = self.empty(2 * k + 4)
+        u = self.empty(4 * k + 8)
         _lib.check(self.lib.mlffpc_precon_apply(self.ctx, _ptr(T), k, 0 if T is None else T.stride(0), float(lam),
-                                                float(sign), _ptr(r), _ptr(out), _ptr(u), _ptr(Mk), self._stream()))
+                                                float(sign), _ptr(r), _ptr(out), _ptr(u), _ptr(Mk), _ptr(E),
+                                                self._stream()))
         return out
 
     # ---- PCG ------------------------------------------------------------------------------
-    def pcg(self, b, lam, tol, maxiter, K_local=None, T=None, precon_sign=1.0, x0=None, want_hist=False, Mk=None):
+    def pcg(self, b, lam, tol, maxiter, K_local=None, T=None, precon_sign=1.0, x0=None, want_hist=False, Mk=None,
+            E=None):
         """Returns (x_local, iters, resid, info, bnrm2[, hist])."""
         k = 0 if T is None else T.shape[0]
         x = torch.zeros(self.n_local, dtype=torch.float64, device=self.device) if x0 is None else x0.clone()
@@ -362,7 +380,8 @@ class Engine(object):
             hist = np.full(int(maxiter) + 1, np.nan)
         _lib.check(self.lib.mlffpc_pcg(
             self.ctx, _ptr(K_local), 0 if K_local is None else K_local.stride(0), float(lam), _ptr(T), k,
-            0 if T is None else T.stride(0), float(precon_sign), _ptr(Mk), _ptr(b), _ptr(x), float(tol), int(maxiter), out,
+            0 if T is None else T.stride(0), float(precon_sign), _ptr(Mk), _ptr(E), _ptr(b), _ptr(x), float(tol),
+            int(maxiter), out,
             hist.ctypes.data_as(ctypes.c_void_p) if hist is not None else ctypes.c_void_p(0), _ptr(ws), nb.value,
             self._stream()))
         self.last_pcg_stats = {'op_ms': float(out[4]), 'op_calls': int(out[5]), 'precon_ms': float(out[6])}

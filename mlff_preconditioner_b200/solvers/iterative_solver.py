@@ -195,25 +195,32 @@ class Iterative(object):
             sync()
             self.timings['pchol_build'] = timeit.default_timer() - start_preconditioner
             info_cholesky = {'time_cholesky': step_s, 'L.shape': (n, k), 'index_columns': idx_t.cpu().numpy()}
-            # (L L^T + lam I)^{-1}: 'woodbury' is the reference's formula (iterative_cholesky.py:141-148);
-            # 'orthonormal' (default) is the same operator evaluated without the 1/lam cancellation
-            form = task.get('precon_form', 'orthonormal')
-            if form not in ('orthonormal', 'woodbury'):
-                raise ValueError("task['precon_form'] must be 'orthonormal' or 'woodbury'")
-            Mk = None
+            # (L L^T + lam I)^{-1} three ways (same operator; they differ in rounding only):
+            #   'woodbury'  (default) the reference's formula (iterative_cholesky.py:141-148) with an accurately
+            #               summed Gram: reproduces the reference's iteration counts where those are well defined
+            #   'projected' orthonormal basis of range(L) + k x k inverse + first-order exact complement projector:
+            #               no 1/lam cancellation, hence no residual plateau; iteration counts <= the reference's
+            #   'orthonormal' the projected form without the defect correction (round 1; kept for A/B runs)
+            form = task.get('precon_form', 'woodbury')
+            if form not in ('orthonormal', 'woodbury', 'projected'):
+                raise ValueError("task['precon_form'] must be 'woodbury', 'projected' or 'orthonormal'")
+            Mk = E = None
             if k == 0:
                 T = None
             elif form == 'woodbury':
                 T = eng.woodbury_factor_(Lt, lam)
             else:
                 try:
-                    T, Mk = eng.orthonormal_factor_(Lt, lam)
+                    if form == 'projected':
+                        T, Mk, E = eng.projected_factor_(Lt, lam)
+                    else:
+                        T, Mk = eng.orthonormal_factor_(Lt, lam)
                 except np.linalg.LinAlgError:
                     # L^T L is numerically singular (pivots far below eps * max): only the shifted Gram of the
                     # reference's formula is positive definite.  Lt is untouched when the first Cholesky fails.
-                    T, Mk, form = eng.woodbury_factor_(Lt, lam), None, 'woodbury'
+                    T, Mk, E, form = eng.woodbury_factor_(Lt, lam), None, None, 'woodbury'
             self.timings['precon_form'] = form
-            P_op = LowRankPreconditioner(eng, T, lam, 1.0, Mk=Mk)
+            P_op = LowRankPreconditioner(eng, T, lam, 1.0, Mk=Mk, E=E)
             inducing_pts_idxs = np.arange(int(break_percentage * n))  # :792
         else:
             raise NotImplementedError(f'str_preconditioner = {str_preconditioner}')
@@ -240,7 +247,7 @@ class Iterative(object):
         res = eng.pcg(
             y_t[eng.row0:eng.row0 + eng.n_local].contiguous(), lam, task['solver_tol'], maxiter,
             K_local=self.K_local, T=P_op.T, precon_sign=P_op.sign, x0=x0, want_hist=bool(task.get('_want_hist')),
-            Mk=P_op.Mk)
+            Mk=P_op.Mk, E=P_op.E)
         x, iters, resid, info, bnrm2 = res[:5]
         if task.get('_want_hist'):
             self.timings['resid_hist_rel'] = res[5] / bnrm2
@@ -305,6 +312,7 @@ class Iterative(object):
                                  'total_time_preconditioner': total_time_preconditioner}
         if str_preconditioner == 'cholesky':
             info_iterative_solver.update(info_cholesky)
+            info_iterative_solver['precon_form'] = self.timings.get('precon_form')
         self.timings.update(solve=total_time_solve, h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes)
         train_rmse = resid / np.sqrt(len(y))
         return alphas, num_iters, resid, train_rmse, inducing_pts_idxs, is_conv, info_iterative_solver

@@ -51,11 +51,13 @@ class LowRankPreconditioner(_DeviceOperator):
     sign = +1: pivoted-Cholesky Woodbury inverse (iterative_cholesky.py:145-148);
     sign = -1: Nystroem operators (iterative_solver.py:315-318, :376-379).
     With ``Mk`` the same inverse is held in an orthonormal basis (``Engine.orthonormal_factor_``):
-    ``a -> sign * ((a - T^T T a)/lam + T^T Mk T a)``."""
+    ``a -> sign * ((a - T^T T a)/lam + T^T Mk T a)``; with ``E = T T^T - I`` as well
+    (``Engine.projected_factor_``) the complement uses the exact projector to first order:
+    ``a -> sign * ((a - T^T (w - E w))/lam + T^T Mk w)``, ``w = T a``."""
 
-    def __init__(self, engine, T, lam, sign, Mk=None):
+    def __init__(self, engine, T, lam, sign, Mk=None, E=None):
         super().__init__(engine)
-        self.T, self.lam, self.sign, self.Mk = T, float(lam), float(sign), Mk
+        self.T, self.lam, self.sign, self.Mk, self.E = T, float(lam), float(sign), Mk, E
 
     def device_apply(self, a):
-        return self.engine.precon_apply(self.T, self.lam, self.sign, a, Mk=self.Mk)
+        return self.engine.precon_apply(self.T, self.lam, self.sign, a, Mk=self.Mk, E=self.E)

@@ -179,25 +179,51 @@ def kernel_matvec(R_desc, R_d_desc, tril_perms_lin, sig, v, chunk=64):
     return vec_dot_d_desc(R_d_desc, Fs_x).ravel()
 
 
-def kernel_matvec_torch_cpu(R_desc_t, Xp_t, R_d_desc, tril_perms_lin, sig, v, batch=256):
-    """Same operator with torch-CPU ops (the reference's fastest CPU route, ``use_torch=True`` with no
-    GPU visible: torchtools.py:64,172-272) -- used only to time the CPU baseline with all host threads."""
+def torch_cpu_batch_size(n_atoms, dim_d, n_perms_times_train, max_memory=2 ** 30 * 32):
+    """Query batch of the reference's torch path without a GPU: 32 GB budget (torchtools.py:100-113) over the
+    per-sample estimate of ``_memory_per_sample`` (:153-167), minus the two resident [S*M, D] tables."""
+    per_sample = ((dim_d * 2 + n_atoms) * 3 + dim_d * 2 + n_perms_times_train * (dim_d + 4)) * 8
+    const = 2 * n_perms_times_train * dim_d * 8
+    return int(max((max_memory - const) // per_sample, 1))
+
+
+def kernel_matvec_torch_cpu(Rs_t, Xp_t, R_d_desc, tril_perms_lin, sig, v, batch=None):
+    """Same operator with torch-CPU ops in the reference's order (``use_torch=True`` with no GPU visible:
+    predict.py:1044-1052 -> torchtools.py:172-272) -- used only to time the CPU baseline with all host threads.
+
+    Like the reference it starts from the Cartesian geometries ``Rs_t[M, N, 3]`` and recomputes the query
+    descriptors (torchtools.py:177-203: pairwise differences, norm, reciprocal of the lower-triangle entries) instead
+    of reusing ``R_desc``; the final ``J^T f`` is the reference's scaled scatter over the difference tensor
+    (:259-263).  One batch of ``torch_cpu_batch_size`` queries at a time (the DataLoader of :299-301)."""
     import torch
 
-    M, D = R_desc_t.shape
+    M, N = Rs_t.shape[:2]
+    D = Xp_t.shape[1]
     q = np.sqrt(5) / sig
     beta = d_desc_dot_vec(R_d_desc, np.asarray(v, dtype=float).reshape(M, -1))  # host numpy, as torchtools.py:145
-    Bp = torch.from_numpy(permuted_rows(beta, tril_perms_lin).reshape(-1, D))
-    out = torch.empty((M, D), dtype=torch.float64)
+    Bp = torch.from_numpy(np.ascontiguousarray(permuted_rows(beta, tril_perms_lin).reshape(-1, D)))
+    if batch is None:
+        batch = torch_cpu_batch_size(N, D, Xp_t.shape[0])
+    lo_a, lo_b = np.tril_indices(N, k=-1)
+    out = []
     for s in range(0, M, batch):
-        x_diffs = (q * R_desc_t[s:s + batch])[:, None, :] - q * Xp_t
+        Rb = Rs_t[s:s + batch]
+        diffs = Rb[:, :, None, :] - Rb[:, None, :, :]                 # [B, N, N, 3]
+        xs = 1 / diffs.norm(dim=-1)[:, lo_a, lo_b]                     # [B, D]
+        x_diffs = (q * xs)[:, None, :] - q * Xp_t                      # [B, S*M, D]
         x_dists = x_diffs.norm(dim=-1)
         exp_xs = 5.0 / (3 * sig ** 2) * torch.exp(-x_dists)
         dot = torch.einsum('ijk,jk->ij', x_diffs, Bp)
+        exp_1_dists = exp_xs * (1 + x_dists)
         f = torch.einsum('ij,ij,ijk->ik', exp_xs, dot, x_diffs)
-        f -= (exp_xs * (1 + x_dists)).mm(Bp)
-        out[s:s + batch] = f
-    return vec_dot_d_desc(R_d_desc, out.numpy()).ravel()
+        del exp_xs, x_diffs
+        f -= exp_1_dists.mm(Bp)
+        f *= xs ** 3
+        diffs[:, lo_a, lo_b, :] *= f[..., None]
+        diffs[:, lo_b, lo_a, :] *= f[..., None]
+        out.append(diffs.sum(dim=1))
+        del diffs
+    return torch.cat(out).numpy().reshape(-1)
 
 
 def kernel_operator(R_desc, R_d_desc, tril_perms_lin, sig, lam):
@@ -301,6 +327,25 @@ def orthonormal_apply_reorth(Qt, Mk, lam, a):
     w2 = Qt @ rp
     rp = rp - Qt.T @ w2
     return rp / lam + Qt.T @ (Mk @ (w + w2))
+
+
+def gram_defect(Qt, chunk=16):
+    """``E = Qt Qt^T - I`` of a numerically orthonormal factor, accumulated beyond fp64 -- numpy restatement of
+    ``mlffpc_gram_defect`` (csrc/gramdd.cu; not in the reference): fp64 products of ``chunk``-column slices (what one
+    DMMA k-tile yields) summed in extended precision.  A plain fp64 Gram's own rounding is as large as E."""
+    k, n = Qt.shape
+    acc = np.zeros((k, k), dtype=np.longdouble)
+    for c in range(0, n, chunk):
+        acc += Qt[:, c:c + chunk] @ Qt[:, c:c + chunk].T
+    return np.asarray(acc - np.eye(k, dtype=np.longdouble), dtype=float)
+
+
+def projected_apply(Qt, Mk, E, lam, a):
+    """Projected form of the same inverse (library ``precon_form='projected'``, csrc/precon.cu): the complement uses
+    the exact projector onto range(Qt^T) to first order, ``Qt^T (I + E)^{-1} Qt ~ Qt^T (I - E) Qt``:
+    ``z = (a - Qt^T (w - E w)) / lam + Qt^T Mk w``,  ``w = Qt a`` -- two passes over the factor."""
+    w = Qt @ a
+    return (a - Qt.T @ (w - E @ w)) / lam + Qt.T @ (Mk @ w)
 
 
 def cho_factor_stable(Mat):
