@@ -373,12 +373,16 @@ def run_ours(args):
     sampler.start()
     launches0 = lib.mlffpc_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev0.record()
-    for _ in range(args.steps):
+    step_ev[0].record()
+    for i in range(args.steps):
         it, out = one_step()
         stats.append((it.timings, out[1], out[2], out[3]))
+        step_ev[i + 1].record()
     ev1.record()
     barrier()
+    step_s = [step_ev[i].elapsed_time(step_ev[i + 1]) * 1e-3 for i in range(args.steps)]
     launches = lib.mlffpc_launch_count() - launches0
     clocks = sampler.stop()
     dev_s = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
@@ -439,7 +443,11 @@ def run_ours(args):
               'assemble_s': tm['assemble'], 'cg_s': tm['cg'], 'cg_iters': iters, 'resid': resid,
               'rel_resid': resid / np.linalg.norm(inp['y']), 'converged': info == 0,
               'precon_apply_avg_ms': pre_ms / max(op_calls, 1),
-              'rel_resid_every_100_iters': [float('%.3g' % v) for v in tm['resid_hist_rel'][::100]]}
+              'rel_resid_every_100_iters': [float('%.3g' % v) for v in tm['resid_hist_rel'][::100]],
+              'per_step': [{'device_s': float('%.4f' % step_s[i]), 'preconditioner_s': float('%.4f' % st[0]['preconditioner']),
+                            'pchol_build_s': float('%.4f' % (st[0].get('pchol_build') or 0.0)),
+                            'assemble_s': float('%.4f' % st[0]['assemble']), 'cg_s': float('%.4f' % st[0]['cg']),
+                            'cg_iters': int(st[1])} for i, st in enumerate(stats)]}
 
     # ---- the same system through the matrix-free operator (one solve, reported next to the headline) ------
     del it, out

@@ -53,6 +53,7 @@ int mlffpc_allgather(mlffpc_ctx* ctx, const void* send, void* recv, int64_t byte
  * and the (R_desc, R_d_desc, tril_perms_lin) arguments every reference routine takes.
  * R_desc[M,D], R_d_desc[M,D,3] fp64; desc_perms[S,D] int32 = pi_p(d) (tril_perms_lin de-linearised,
  * train.py:783-790); atom_perms[S,N] int32 = task['perms'].  The input buffers must stay alive.
+ * R_d_desc may be NULL for a prediction-only context (mlffpc_predict with beta).
  * [pt0, pt1) is this context's row block of training points (whole range for one GPU). */
 int mlffpc_geometry_workspace_bytes(int64_t M, int N, int S, int64_t* bytes);
 int mlffpc_set_geometry(mlffpc_ctx* ctx, int64_t M, int N, int S, const double* R_desc,
@@ -136,6 +137,27 @@ int mlffpc_matvec_free_workspace_bytes(mlffpc_ctx* ctx, int64_t* bytes);
 int mlffpc_matvec_free(mlffpc_ctx* ctx, const double* v, double* y_local, double alpha, double shift,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------- prediction / caller-side prep ---- */
+/* Descriptors and compressed Jacobians of B geometries R[B, N, 3] (device): R_desc[B, D] = 1 / |r_a - r_b|,
+ * R_d_desc[B, D, 3] = (r_a - r_b) / |r_a - r_b|^3 over the pairs d <-> (a_d > b_d) of np.tril_indices(N, -1).
+ * Replaces Desc.from_R (utils/desc.py:292-358, workers :112-200) -- one-off host prep of GDMLTrain.train
+ * (train.py:813-819) and of every prediction (predict.py:1083).  No geometry needs to be set. */
+int mlffpc_desc_from_r(mlffpc_ctx* ctx, const double* R, int64_t B, int N, double* R_desc, double* R_d_desc, void* stream);
+/* out[M, D] = J_m v_m for the full n-vector v: beta of the matvec and the model's R_d_desc_alpha.  Replaces
+ * desc.d_desc_dot_vec (utils/desc.py:394-405) in GDMLTrain.create_model (train.py:640-645). */
+int mlffpc_d_desc_dot_vec(mlffpc_ctx* ctx, const double* v, double* out, void* stream);
+/* Energies and forces of B query geometries from the model whose training geometry is set in ctx and whose
+ * coefficients are given either as v = alphas_F[n] (beta = NULL) or as beta[M, D] = J_j alpha_j = model['R_d_desc_alpha']
+ * (v = NULL; train.py:640-645 -- then the context may have been set without R_d_desc):   F_out[B, 3N] = J_q^T f_q  and  E_out[B] = sum_jp e^(1 + rho^) (Delta . beta_jp)
+ * (unscaled: the caller applies model['std'] and model['c']).  Replaces GDMLPredict.predict for arbitrary queries
+ * (predict.py:997-1110 -> _predict_wkr :72-234 / GDMLTorchPredict._forward torchtools.py:172-272, incl. the energy
+ * einsum :268) and, with the training geometries as queries, the energy pass of GDMLTrain._recov_int_const
+ * (train.py:972-1119).  E_out may be NULL.  Rq_desc / Rq_d_desc as produced by mlffpc_desc_from_r. */
+int mlffpc_predict_workspace_bytes(mlffpc_ctx* ctx, int64_t B, int64_t* bytes);
+int mlffpc_predict(mlffpc_ctx* ctx, const double* Rq_desc, const double* Rq_d_desc, int64_t B, const double* v,
+                   const double* beta, double* F_out, double* E_out, void* workspace, int64_t workspace_bytes,
+                   void* stream);
+
 /* ---------------------------------------------------------------- dense building blocks ---- */
 /* Row-major fp64 GEMM on the FP64 tensor pipe (DMMA): C = alpha * A * op(B) + beta * C,
  * A[m,k], op(B) = B[k,n] (trans_b = 0) or B[n,k]^T (trans_b = 1).  Stands in for the host BLAS calls
@@ -217,14 +239,17 @@ int mlffpc_precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld,
  *   out_host[8] (host doubles): iterations, final ||r||, info (0 converged), ||b||,
  *       summed operator ms, operator calls, summed preconditioner ms (CUDA events), reserved
  *   resid_hist_host: NULL or host double[maxiter+1] receiving ||r|| per iteration
+ *   resume_iters: 0, or the iteration count a previous call with the SAME workspace and x stopped at (its maxiter):
+ *       the run continues with the saved r, p, rho -- one uninterrupted recurrence cut into checkpoint segments
+ *       (the reference writes an unconverged model every ~2 minutes from scipy's callback, iterative_solver.py:919-954)
  * The stopping test runs on the device; the host reads the loop state one batch of iterations late and never waits
  * for a scalar inside the loop (csrc/pcg.cu).  Iteration count, x and r are those of the legacy loop.
  * Workspace: mlffpc_pcg_workspace_bytes. */
 int mlffpc_pcg_workspace_bytes(mlffpc_ctx* ctx, int64_t k, int matrix_free, int64_t* bytes);
 int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam, const double* T,
                int64_t k, int64_t ld_t, double precon_sign, const double* Mk, const double* E, const double* b,
-               double* x, double tol, int64_t maxiter, double* out_host, double* resid_hist_host, void* workspace,
-               int64_t workspace_bytes, void* stream);
+               double* x, double tol, int64_t maxiter, int64_t resume_iters, double* out_host, double* resid_hist_host,
+               void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- small vector helpers ---- */
 /* out[i] = X[rows[i], :] gathered rows etc. are done with torch indexing on the host side; the only

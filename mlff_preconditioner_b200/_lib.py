@@ -47,6 +47,10 @@ SIGNATURES = {
     'mlffpc_symop_apply': [c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_i64, c_ptr, c_ptr],
     'mlffpc_matvec_free_workspace_bytes': [c_ptr, ctypes.POINTER(c_i64)],
     'mlffpc_matvec_free': [c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr, c_i64, c_ptr],
+    'mlffpc_desc_from_r': [c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr],
+    'mlffpc_d_desc_dot_vec': [c_ptr, c_ptr, c_ptr, c_ptr],
+    'mlffpc_predict_workspace_bytes': [c_ptr, c_i64, ctypes.POINTER(c_i64)],
+    'mlffpc_predict': [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     'mlffpc_dgemm': [c_ptr, c_int, c_i64, c_i64, c_i64, c_dbl, c_ptr, c_i64, c_ptr, c_i64, c_dbl, c_ptr,
                      c_i64, c_ptr],
     'mlffpc_syrk_rows': [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_dbl, c_ptr, c_i64, c_ptr],
@@ -61,7 +65,7 @@ SIGNATURES = {
     'mlffpc_precon_apply': [c_ptr, c_ptr, c_i64, c_i64, c_dbl, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     'mlffpc_pcg_workspace_bytes': [c_ptr, c_i64, c_int, ctypes.POINTER(c_i64)],
     'mlffpc_pcg': [c_ptr, c_ptr, c_i64, c_dbl, c_ptr, c_i64, c_i64, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_i64,
-                   c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
+                   c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     'mlffpc_dot': [c_ptr, c_ptr, c_ptr, c_i64, ctypes.POINTER(c_dbl), c_ptr],
 }
 NON_INT_RETURNS = {'mlffpc_version': (c_int, []), 'mlffpc_last_error': (c_str, []),

@@ -466,8 +466,9 @@ int mlffpc_set_geometry(mlffpc_ctx* ctx, int64_t M, int N, int S, const double* 
                         const double* R_d_desc, const int32_t* desc_perms, const int32_t* atom_perms,
                         double sig, int64_t pt0, int64_t pt1, void* workspace, int64_t workspace_bytes,
                         void* stream) {
-    MLFFPC_REQUIRE(ctx && R_desc && R_d_desc && desc_perms && atom_perms && workspace,
-                   "set_geometry: NULL argument");
+    // R_d_desc may be NULL for a prediction-only context (mlffpc_predict with beta); everything that needs the
+    // training Jacobians checks for it
+    MLFFPC_REQUIRE(ctx && R_desc && desc_perms && atom_perms && workspace, "set_geometry: NULL argument");
     MLFFPC_REQUIRE(M > 0 && N >= 2 && S >= 1 && sig > 0, "set_geometry: bad sizes (M=%lld N=%d S=%d sig=%g)",
                    (long long)M, N, S, sig);
     MLFFPC_REQUIRE(0 <= pt0 && pt0 < pt1 && pt1 <= M, "set_geometry: bad shard [%lld, %lld) of %lld",
@@ -505,6 +506,7 @@ int mlffpc_set_geometry(mlffpc_ctx* ctx, int64_t M, int N, int S, const double* 
 
 int mlffpc_kernel_diag(mlffpc_ctx* ctx, double* out, void* stream) {
     MLFFPC_REQUIRE(ctx && out && ctx->M > 0, "kernel_diag: geometry not set or NULL output");
+    MLFFPC_REQUIRE(ctx->R_d_desc, "kernel_diag: geometry was set without R_d_desc");
     GeoView g = make_view(ctx);
     const size_t smem = (size_t)(2 * g.S + 40 + 2 * g.S * g.dim_i) * sizeof(double);
     MLFFPC_REQUIRE(smem <= 200 * 1024, "kernel_diag: S*3N = %d too large for shared memory", g.S * g.dim_i);
@@ -538,6 +540,7 @@ int mlffpc_kernel_columns(mlffpc_ctx* ctx, const int64_t* cols, int64_t b, doubl
     MLFFPC_REQUIRE(ctx && ctx->M > 0, "kernel_columns: geometry not set");
     if (b == 0) return MLFFPC_OK;
     MLFFPC_REQUIRE(cols && out && b > 0, "kernel_columns: NULL argument");
+    MLFFPC_REQUIRE(ctx->R_d_desc, "kernel_columns: geometry was set without R_d_desc");
     MLFFPC_REQUIRE(ld >= ctx->n_local(), "kernel_columns: ld %lld < n_local %lld", (long long)ld, (long long)ctx->n_local());
     GeoView g = make_view(ctx);
     const size_t smem = (size_t)(2 * g.S + 40 + g.S) * sizeof(double);
@@ -563,6 +566,7 @@ int assemble_tile(mlffpc_ctx* ctx, int64_t i_pt0, int64_t i_pt1, int64_t j_pt0, 
                    "assemble_tile: bad point ranges");
     MLFFPC_REQUIRE(packed ? (i_pt0 == j_pt0 && i_pt1 == j_pt1) : (ld >= (j_pt1 - j_pt0) * ctx->dim_i),
                    "assemble_tile: ld too small / packed layout needs a square diagonal tile");
+    MLFFPC_REQUIRE(ctx->R_d_desc, "assemble_tile: geometry was set without R_d_desc");
     GeoView g = make_view(ctx);
     const int64_t ni = i_pt1 - i_pt0, nj = j_pt1 - j_pt0;
     // row-walking kernel: JT column points per CTA so that one CTA covers ~256 output columns

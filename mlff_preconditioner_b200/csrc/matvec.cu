@@ -15,7 +15,7 @@ __global__ void mv_prepare_kernel(int64_t MS, int S, int D, int N, int64_t ldb,
                                   const double* __restrict__ Xp, const double* __restrict__ R_d_desc,
                                   const int32_t* __restrict__ desc_perms, const int32_t* __restrict__ pair_a,
                                   const int32_t* __restrict__ pair_b, const double* __restrict__ v,
-                                  double* __restrict__ Bmat) {
+                                  const double* __restrict__ beta_in, double* __restrict__ Bmat) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = MS * (D + 1);
     if (t >= total) return;
@@ -29,11 +29,16 @@ __global__ void mv_prepare_kernel(int64_t MS, int S, int D, int N, int64_t ldb,
     const int p = (int)(jp % S);
     const int64_t j = jp / S;
     const int e = desc_perms[p * D + d];
-    const int a = pair_a[e], b = pair_b[e];
-    const double* g = R_d_desc + (j * D + e) * 3;
-    const double* vj = v + j * 3 * N;
-    const double beta = g[0] * (vj[3 * b] - vj[3 * a]) + g[1] * (vj[3 * b + 1] - vj[3 * a + 1]) +
-                        g[2] * (vj[3 * b + 2] - vj[3 * a + 2]);
+    double beta;
+    if (beta_in) {  // beta_j = J_j alpha_j given (model['R_d_desc_alpha'], train.py:640-645)
+        beta = beta_in[j * D + e];
+    } else {
+        const int a = pair_a[e], b = pair_b[e];
+        const double* g = R_d_desc + (j * D + e) * 3;
+        const double* vj = v + j * 3 * N;
+        beta = g[0] * (vj[3 * b] - vj[3 * a]) + g[1] * (vj[3 * b + 1] - vj[3 * a + 1]) +
+               g[2] * (vj[3 * b + 2] - vj[3 * a + 2]);
+    }
     Bmat[jp * ldb + d] = Xp[jp * D + d];
     Bmat[(MS + jp) * ldb + d] = beta;
 }
@@ -43,7 +48,8 @@ constexpr int PDC = 16;   // descriptor chunk
 
 __global__ void __launch_bounds__(256)
 mv_pairs_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __restrict__ Bmat, int64_t ldb,
-                int64_t MS, int D, double q, double pref, double* __restrict__ Cmat, int64_t ldc) {
+                int64_t MS, int D, double q, double pref, double* __restrict__ Cmat, int64_t ldc,
+                double* __restrict__ Epart) {
     __shared__ double xq[PDC][PT + 2], xj[PDC][PT + 2], bj[PDC][PT + 2];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int64_t i0 = (int64_t)blockIdx.y * PT, j0 = (int64_t)blockIdx.x * PT;
@@ -87,25 +93,42 @@ mv_pairs_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __restr
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int64_t i = i0 + ty * 4 + a;
-        if (i >= Ml) continue;
+        double esum = 0.0;  // energy: sum_j e^ (1 + rho^) (Delta . beta)   (torchtools.py:268, predict.py:207)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int64_t j = j0 + tx + 16 * b;
-            if (j >= MS) continue;
+            if (i >= Ml || j >= MS) continue;
             const double rho = q * sqrt(s2[a][b]);
             const double e = pref * exp(-rho);
+            const double c2 = e * (1.0 + rho);
             Cmat[i * ldc + j] = e * q2 * tt[a][b];
-            Cmat[i * ldc + MS + j] = e * (1.0 + rho);
+            Cmat[i * ldc + MS + j] = c2;
+            esum = fma(c2, tt[a][b], esum);
+        }
+        if (Epart) {  // the 16 threads of a row sit in one half-warp
+            esum += __shfl_xor_sync(0xffffffffu, esum, 8);
+            esum += __shfl_xor_sync(0xffffffffu, esum, 4);
+            esum += __shfl_xor_sync(0xffffffffu, esum, 2);
+            esum += __shfl_xor_sync(0xffffffffu, esum, 1);
+            if (tx == 0 && i < Ml) Epart[i * gridDim.x + blockIdx.x] = esum;
         }
     }
 }
 
 // CTA per local point: G = sum of the split-K partials; f = G[i,D] x_i - G[i,:D];  y = alpha J_i^T f + shift v_local
+// R_desc / R_d_desc / v are indexed by pt0 + il (training mode: the context's tables; prediction: the query tables with
+// pt0 = 0).  Epart != NULL: E[il] = sum of the pair kernel's per-tile energy partials (fixed order).
 __global__ void mv_epilogue_kernel(int N, int D, int64_t pt0, const double* __restrict__ R_desc,
                                    const double* __restrict__ R_d_desc, double* __restrict__ G,
                                    int64_t ldg, int nsplit, int64_t zstride, const double* __restrict__ v,
-                                   double* __restrict__ y, double alpha, double shift) {
+                                   double* __restrict__ y, double alpha, double shift,
+                                   const double* __restrict__ Epart, int n_epart, double* __restrict__ E_out) {
     const int64_t il = blockIdx.x, i = pt0 + il;
+    if (Epart && threadIdx.x == 0) {
+        double e = 0.0;
+        for (int c = 0; c < n_epart; ++c) e += Epart[il * n_epart + c];
+        E_out[il] = alpha * e;
+    }
     const double* xi = R_desc + i * D;
     const double* gi = R_d_desc + i * D * 3;
     double* Gi = G + il * ldg;
@@ -176,18 +199,112 @@ int matvec_free(mlffpc_ctx* ctx, const double* v, double* y_local, double alpha,
 
     const int64_t total = MS * (D + 1);
     mv_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(MS, ctx->S, D, N, w.ldb, ctx->Xp, ctx->R_d_desc,
-                                                                     ctx->desc_perms, ctx->pair_a, ctx->pair_b, v, Bmat);
+                                                                     ctx->desc_perms, ctx->pair_a, ctx->pair_b, v, nullptr, Bmat);
     MLFFPC_LAUNCH_CHECK();
     dim3 grid((unsigned)((MS + PT - 1) / PT), (unsigned)((Ml + PT - 1) / PT));
     MLFFPC_REQUIRE(grid.y <= 65535, "matvec_free: too many local points for this launch shape");
-    mv_pairs_kernel<<<grid, 256, 0, s>>>(ctx->R_desc + ctx->pt0 * D, Ml, Bmat, w.ldb, MS, D, q, pref, Cmat, 2 * MS);
+    mv_pairs_kernel<<<grid, 256, 0, s>>>(ctx->R_desc + ctx->pt0 * D, Ml, Bmat, w.ldb, MS, D, q, pref, Cmat, 2 * MS, nullptr);
     MLFFPC_LAUNCH_CHECK();
     MLFFPC_TRY(dgemm(false, Ml, D + 1, 2 * MS, 1.0, Cmat, 2 * MS, Bmat, w.ldb, 0.0, G, w.ldb, false, s, w.nsplit,
                      Ml * w.ldb));
     int block = 32;
     while (block < 3 * N && block < 256) block <<= 1;
     mv_epilogue_kernel<<<(unsigned)Ml, block, 0, s>>>(N, D, ctx->pt0, ctx->R_desc, ctx->R_d_desc, G, w.ldb, w.nsplit,
-                                                     Ml * w.ldb, v, y_local, alpha, shift);
+                                                     Ml * w.ldb, v, y_local, alpha, shift, nullptr, 0, nullptr);
+    MLFFPC_LAUNCH_CHECK();
+    return MLFFPC_OK;
+}
+
+// ---- prediction for arbitrary query geometries (GDMLPredict.predict, predict.py:997-1110; torchtools.py:172-272) ----
+// Descriptor x_d = 1 / |r_a - r_b| and its compressed Jacobian g_d = (r_a - r_b) / |r_a - r_b|^3 for the pairs
+// d <-> (a_d > b_d) in np.tril_indices order (utils/desc.py:112-200, :292-358).  One thread per (geometry, pair).
+__global__ void desc_from_r_kernel(const double* __restrict__ R, int64_t B, int N, int D, double* __restrict__ R_desc,
+                                   double* __restrict__ R_d_desc) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * D) return;
+    const int64_t m = t / D;
+    const int d = (int)(t % D);
+    int a = (int)((1.0 + sqrt(1.0 + 8.0 * (double)d)) * 0.5);
+    while (a * (a - 1) / 2 > d) --a;
+    while ((a + 1) * a / 2 <= d) ++a;
+    const int b = d - a * (a - 1) / 2;
+    const double* ra = R + (m * N + a) * 3;
+    const double* rb = R + (m * N + b) * 3;
+    const double dx = ra[0] - rb[0], dy = ra[1] - rb[1], dz = ra[2] - rb[2];
+    // no FMA contraction: the same roundings as the host's sum of squares
+    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    const double r = sqrt(r2);
+    const double r3 = __dmul_rn(__dmul_rn(r, r), r);
+    R_desc[t] = 1.0 / r;
+    R_d_desc[t * 3 + 0] = dx / r3;
+    R_d_desc[t * 3 + 1] = dy / r3;
+    R_d_desc[t * 3 + 2] = dz / r3;
+}
+
+// beta[m, d] = g[m, d, :] . (v[m, b_d, :] - v[m, a_d, :])   (desc.d_desc_dot_vec, utils/desc.py:394-405; the
+// model's R_d_desc_alpha, train.py:640-645)
+__global__ void jv_kernel(int64_t M, int D, int N, const double* __restrict__ R_d_desc, const int32_t* __restrict__ pair_a,
+                          const int32_t* __restrict__ pair_b, const double* __restrict__ v, double* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M * D) return;
+    const int64_t m = t / D;
+    const int d = (int)(t % D);
+    const int a = pair_a[d], b = pair_b[d];
+    const double* g = R_d_desc + t * 3;
+    const double* vm = v + m * 3 * N;
+    out[t] = g[0] * (vm[3 * b] - vm[3 * a]) + g[1] * (vm[3 * b + 1] - vm[3 * a + 1]) + g[2] * (vm[3 * b + 2] - vm[3 * a + 2]);
+}
+
+struct PredWs {
+    int64_t ldb, off_bmat, off_cmat, off_g, off_epart, total;
+    int nsplit, ncb;
+};
+static PredWs pred_layout(const mlffpc_ctx* c, int64_t B) {
+    auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+    PredWs w;
+    const int64_t MS = c->M * c->S;
+    w.ldb = (c->D + 2) & ~(int64_t)1;
+    int64_t o = 0;
+    w.off_bmat = o; o = up(o + 2 * MS * w.ldb * 8);
+    w.off_cmat = o; o = up(o + B * 2 * MS * 8);
+    const int64_t tiles = ((B + 127) / 128) * ((c->D + 1 + 127) / 128);
+    int64_t ns = (2 * (int64_t)c->num_sms + tiles - 1) / tiles;
+    const int64_t max_by_k = (2 * MS) / 512;
+    if (ns > max_by_k) ns = max_by_k;
+    if (ns > 32) ns = 32;
+    if (ns < 1) ns = 1;
+    w.nsplit = (int)ns;
+    w.off_g = o; o = up(o + ns * B * w.ldb * 8);
+    w.ncb = (int)((MS + PT - 1) / PT);
+    w.off_epart = o; o = up(o + B * w.ncb * 8);
+    w.total = o + 256;
+    return w;
+}
+
+int predict(mlffpc_ctx* ctx, const double* Rq_desc, const double* Rq_d_desc, int64_t B, const double* v,
+            const double* beta, double* F_out, double* E_out, void* workspace, cudaStream_t s) {
+    const PredWs w = pred_layout(ctx, B);
+    char* base = (char*)(((uintptr_t)workspace + 255) / 256 * 256);
+    double* Bmat = (double*)(base + w.off_bmat);
+    double* Cmat = (double*)(base + w.off_cmat);
+    double* G = (double*)(base + w.off_g);
+    double* Epart = (double*)(base + w.off_epart);
+    const int64_t MS = ctx->M * ctx->S;
+    const int D = ctx->D, N = ctx->N;
+    const double q = sqrt(5.0) / ctx->sig, pref = 5.0 / (3.0 * ctx->sig * ctx->sig);
+    const int64_t total = MS * (D + 1);
+    mv_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(MS, ctx->S, D, N, w.ldb, ctx->Xp, ctx->R_d_desc,
+                                                                     ctx->desc_perms, ctx->pair_a, ctx->pair_b, v, beta, Bmat);
+    MLFFPC_LAUNCH_CHECK();
+    dim3 grid((unsigned)w.ncb, (unsigned)((B + PT - 1) / PT));
+    MLFFPC_REQUIRE(grid.y <= 65535, "predict: too many query geometries in one call (%lld)", (long long)B);
+    mv_pairs_kernel<<<grid, 256, 0, s>>>(Rq_desc, B, Bmat, w.ldb, MS, D, q, pref, Cmat, 2 * MS, E_out ? Epart : nullptr);
+    MLFFPC_LAUNCH_CHECK();
+    MLFFPC_TRY(dgemm(false, B, D + 1, 2 * MS, 1.0, Cmat, 2 * MS, Bmat, w.ldb, 0.0, G, w.ldb, false, s, w.nsplit, B * w.ldb));
+    int block = 32;
+    while (block < 3 * N && block < 256) block <<= 1;
+    mv_epilogue_kernel<<<(unsigned)B, block, 0, s>>>(N, D, 0, Rq_desc, Rq_d_desc, G, w.ldb, w.nsplit, B * w.ldb, nullptr,
+                                                    F_out, 1.0, 0.0, E_out ? Epart : nullptr, w.ncb, E_out);
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;
 }
@@ -204,10 +321,48 @@ int mlffpc_matvec_free_workspace_bytes(mlffpc_ctx* ctx, int64_t* bytes) {
     return MLFFPC_OK;
 }
 
+int mlffpc_desc_from_r(mlffpc_ctx* ctx, const double* R, int64_t B, int N, double* R_desc, double* R_d_desc, void* stream) {
+    MLFFPC_REQUIRE(ctx && R && R_desc && R_d_desc && B >= 0 && N >= 2, "desc_from_r: bad argument");
+    const int D = N * (N - 1) / 2;
+    const int64_t total = B * D;
+    if (total == 0) return MLFFPC_OK;
+    desc_from_r_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(R, B, N, D, R_desc, R_d_desc);
+    MLFFPC_LAUNCH_CHECK();
+    return MLFFPC_OK;
+}
+
+int mlffpc_d_desc_dot_vec(mlffpc_ctx* ctx, const double* v, double* out, void* stream) {
+    MLFFPC_REQUIRE(ctx && ctx->M > 0 && v && out, "d_desc_dot_vec: geometry not set or NULL argument");
+    MLFFPC_REQUIRE(ctx->R_d_desc, "d_desc_dot_vec: geometry was set without R_d_desc");
+    const int64_t total = ctx->M * ctx->D;
+    jv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ctx->M, ctx->D, ctx->N, ctx->R_d_desc,
+                                                                                  ctx->pair_a, ctx->pair_b, v, out);
+    MLFFPC_LAUNCH_CHECK();
+    return MLFFPC_OK;
+}
+
+int mlffpc_predict_workspace_bytes(mlffpc_ctx* ctx, int64_t B, int64_t* bytes) {
+    MLFFPC_REQUIRE(ctx && bytes && B > 0 && ctx->M > 0, "predict_workspace_bytes: bad argument / geometry not set");
+    *bytes = pred_layout(ctx, B).total;
+    return MLFFPC_OK;
+}
+
+int mlffpc_predict(mlffpc_ctx* ctx, const double* Rq_desc, const double* Rq_d_desc, int64_t B, const double* v,
+                   const double* beta, double* F_out, double* E_out, void* workspace, int64_t workspace_bytes,
+                   void* stream) {
+    MLFFPC_REQUIRE(ctx && ctx->M > 0, "predict: geometry not set");
+    MLFFPC_REQUIRE(Rq_desc && Rq_d_desc && F_out && workspace && B > 0, "predict: bad argument");
+    MLFFPC_REQUIRE((v != nullptr) != (beta != nullptr), "predict: give exactly one of v (alphas) and beta (R_d_desc_alpha)");
+    MLFFPC_REQUIRE(beta || ctx->R_d_desc, "predict: coefficients v need the training Jacobians (geometry was set without R_d_desc)");
+    MLFFPC_REQUIRE(workspace_bytes >= pred_layout(ctx, B).total, "predict: workspace too small");
+    return predict(ctx, Rq_desc, Rq_d_desc, B, v, beta, F_out, E_out, workspace, (cudaStream_t)stream);
+}
+
 int mlffpc_matvec_free(mlffpc_ctx* ctx, const double* v, double* y_local, double alpha, double shift,
                        void* workspace, int64_t workspace_bytes, void* stream) {
     MLFFPC_REQUIRE(ctx && ctx->M > 0, "matvec_free: geometry not set");
     MLFFPC_REQUIRE(v && y_local && workspace, "matvec_free: NULL argument");
+    MLFFPC_REQUIRE(ctx->R_d_desc, "matvec_free: geometry was set without R_d_desc");
     MLFFPC_REQUIRE(workspace_bytes >= matvec_free_ws_bytes(ctx), "matvec_free: workspace too small");
     return matvec_free(ctx, v, y_local, alpha, shift, workspace, (cudaStream_t)stream);
 }

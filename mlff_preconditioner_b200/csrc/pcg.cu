@@ -234,8 +234,8 @@ int mlffpc_pcg_workspace_bytes(mlffpc_ctx* ctx, int64_t k, int matrix_free, int6
 
 int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam, const double* T,
                int64_t k, int64_t ld_t, double precon_sign, const double* Mk, const double* E, const double* b,
-               double* x, double tol, int64_t maxiter, double* out_host, double* resid_hist_host, void* workspace,
-               int64_t workspace_bytes, void* stream) {
+               double* x, double tol, int64_t maxiter, int64_t resume_iters, double* out_host, double* resid_hist_host,
+               void* workspace, int64_t workspace_bytes, void* stream) {
     MLFFPC_REQUIRE(ctx && ctx->M > 0, "pcg: geometry not set");
     MLFFPC_REQUIRE(b && x && out_host && workspace, "pcg: NULL argument");
     MLFFPC_REQUIRE(lam > 0.0 && tol > 0.0 && maxiter >= 0, "pcg: bad lam/tol/maxiter");
@@ -244,6 +244,7 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     MLFFPC_REQUIRE(!ctx->use_symv || ctx->lay_world == ctx->comm.world, "pcg: symmetric tile layout does not match the communicator");
     MLFFPC_REQUIRE(!T || (k > 0 && ld_t >= ctx->n_local()), "pcg: bad preconditioner dimensions");
     MLFFPC_REQUIRE(!E || Mk, "pcg: the defect matrix E needs the orthonormal-form Mk");
+    MLFFPC_REQUIRE(resume_iters >= 0 && resume_iters <= maxiter, "pcg: resume_iters out of range");
     const bool matrix_free = (K_local == nullptr);
     if (T && Mk) MLFFPC_TRY(ensure_reorth_scratch(ctx, k));
     const PcgWs w = pcg_layout(ctx, T ? k : 0, matrix_free);
@@ -302,7 +303,11 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
         return MLFFPC_OK;
     };
 
-    MLFFPC_CUDA(cudaMemsetAsync(base + w.off_state, 0, 256, s));
+    // resume_iters > 0: continue the run whose state (r, p, rho, x, history) the previous call left in this workspace
+    // after stopping at its iteration cap -- same recurrence, no restart (checkpoint segments of Iterative.solve)
+    const bool resume = resume_iters > 0;
+    if (!resume) MLFFPC_CUDA(cudaMemsetAsync(base + w.off_state, 0, 256, s));
+    else MLFFPC_CUDA(cudaMemsetAsync(state, 0, sizeof(PcgState), s));
     double bb = 0.0;
     dot_kernel<<<g, VEC_THREADS, 0, s>>>(b, b, nl, ctx->partials, counter, sc + S_TMP, nullptr);
     MLFFPC_LAUNCH_CHECK();
@@ -311,18 +316,18 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     const double bnrm2 = sqrt(bb);
 
     double resid = 0.0;
-    MLFFPC_TRY(true_residual());
+    if (!resume) MLFFPC_TRY(true_residual());
     MLFFPC_TRY(global_resid(&resid));
     out_host[3] = bnrm2;
     out_host[4] = out_host[5] = out_host[6] = out_host[7] = 0.0;
-    if (resid_hist_host) resid_hist_host[0] = resid;
-    if (resid <= tol) {  // legacy _get_atol probe
+    if (resid_hist_host && !resume) resid_hist_host[0] = resid;
+    if (!resume && resid <= tol) {  // legacy _get_atol probe
         out_host[0] = 0; out_host[1] = resid; out_host[2] = 0;
         return MLFFPC_OK;
     }
     const double atol = (bnrm2 == 0.0) ? tol : tol * bnrm2;
     const double atol2 = atol * atol;
-    if (world > 1) MLFFPC_CUDA(cudaMemsetAsync(p_full, 0, (size_t)world * w.n_pad * 8, s));
+    if (world > 1 && !resume) MLFFPC_CUDA(cudaMemsetAsync(p_full, 0, (size_t)world * w.n_pad * 8, s));
 
     // batches of iterations; the state of batch i is read while batch i + 1 runs
     constexpr int BATCH = 4, SLOTS = 2;
@@ -381,12 +386,12 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
         return MLFFPC_OK;
     };
 
-    if (maxiter == 0) {
-        out_host[0] = 0; out_host[1] = resid; out_host[2] = 1;
+    if (maxiter == resume_iters) {
+        out_host[0] = (double)resume_iters; out_host[1] = resid; out_host[2] = 1;
         return MLFFPC_OK;
     }
     ProfGuard prof{prof_window("pcg")};
-    int64_t launched = 0;      // iterations launched so far
+    int64_t launched = resume_iters;  // iterations launched so far
     int64_t it = 0;            // result: iterations the legacy loop would have run
     int info = (int)(maxiter > 0x7fffffff ? 0x7fffffff : maxiter);
     if (info == 0) info = 1;

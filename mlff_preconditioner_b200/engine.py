@@ -43,31 +43,90 @@ def atom_perms_from_desc_perms(desc_perms, n_atoms):
     return out
 
 
+def desc_from_R_device(lib, ctx, R, n_atoms, device, stream):
+    """Device ``Desc.from_R`` (utils/desc.py:292-358) through mlffpc_desc_from_r; R: host array or device tensor."""
+    if not torch.is_tensor(R):
+        R = torch.as_tensor(np.ascontiguousarray(R, dtype=np.float64), device=device)
+    R = R.to(device=device, dtype=torch.float64).reshape(-1, n_atoms, 3).contiguous()
+    Bq = R.shape[0]
+    D = n_atoms * (n_atoms - 1) // 2
+    R_desc = torch.empty((Bq, D), dtype=torch.float64, device=device)
+    R_d_desc = torch.empty((Bq, D, 3), dtype=torch.float64, device=device)
+    _lib.check(lib.mlffpc_desc_from_r(ctx, _ptr(R), Bq, int(n_atoms), _ptr(R_desc), _ptr(R_d_desc), stream))
+    return R_desc, R_d_desc
+
+
+def descriptors_on_device(R, device=None):
+    """(R_desc[M, D], R_d_desc[M, D, 3]) as CUDA tensors for geometries R[M, N, 3] -- ``Desc.from_R`` without an
+    Engine (a short-lived context; the kernel needs no geometry tables)."""
+    if not torch.cuda.is_available():
+        raise _lib.MlffpcError('mlff_preconditioner_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    lib = _lib.load()
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+    n_atoms = (R.shape[-2] if R.ndim == 3 else None) if not torch.is_tensor(R) else (R.shape[-2] if R.dim() == 3 else None)
+    if n_atoms is None:
+        raise ValueError('R must have shape [M, N, 3]')
+    ctx = ctypes.c_void_p()
+    _lib.check(lib.mlffpc_create(ctypes.byref(ctx), dev.index))
+    try:
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        out = desc_from_R_device(lib, ctx, R, n_atoms, dev, stream)
+        torch.cuda.current_stream(dev).synchronize()
+    finally:
+        lib.mlffpc_destroy(ctx)
+    return out
+
+
 def shard_points(M, rank, world):
     """Row-block partition by training points: rank r owns [r*ceil(M/W), min((r+1)*ceil(M/W), M))."""
     ppr = (M + world - 1) // world
-    pt0, pt1 = rank * ppr, min((rank + 1) * ppr, M)
-    if pt0 >= pt1:
-        raise ValueError('more ranks (%d) than training-point blocks (M = %d)' % (world, M))
-    return pt0, pt1
+    # decided from (M, world) alone so that EVERY rank raises -- a rank-local check would leave the other ranks
+    # blocked in their first collective
+    if (world - 1) * ppr >= M:
+        raise ValueError('%d ranks leave rank %d without training points (M = %d, %d points per rank): use at most %d '
+                         'ranks' % (world, world - 1, M, ppr, (M + ppr - 1) // ppr))
+    return rank * ppr, min((rank + 1) * ppr, M)
 
 
 class Engine(object):
     """Geometry-bound solver context on one GPU (one rank of a row-block sharded job)."""
 
     def __init__(self, R_desc, R_d_desc, tril_perms_lin, sig, perms=None, device=None, rank=0, world=1,
-                 init_comm=None):
+                 init_comm=None, R=None):
+        """``R_desc[M, D]`` / ``R_d_desc[M, D, 3]``: host arrays (uploaded) or CUDA tensors (used in place).
+        ``R_d_desc=None`` makes a prediction-only context (no assembly / matvec with alphas).  With ``R[M, N, 3]``
+        (and ``R_desc=None``) the descriptors are computed on the device (mlffpc_desc_from_r)."""
         if not torch.cuda.is_available():
             raise _lib.MlffpcError('mlff_preconditioner_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
         self.lib = _lib.load()
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
         torch.cuda.set_device(self.device)
         self.rank, self.world = rank, world
-        R_desc = np.ascontiguousarray(R_desc, dtype=np.float64)
-        R_d_desc = np.ascontiguousarray(R_d_desc, dtype=np.float64)
-        self.M, self.D = R_desc.shape
+        ctx = ctypes.c_void_p()
+        _lib.check(self.lib.mlffpc_create(ctypes.byref(ctx), self.device.index))
+        self.ctx = ctx
+        self.h2d_bytes = 0
+
+        def to_dev(a):
+            if torch.is_tensor(a):
+                return a.to(device=self.device, dtype=torch.float64).contiguous()
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            self.h2d_bytes += a.nbytes
+            return torch.from_numpy(a).to(self.device)
+
+        if R_desc is None:
+            if R is None:
+                raise ValueError('Engine needs descriptors (R_desc, R_d_desc) or geometries (R)')
+            Rt = to_dev(R)
+            n_atoms = Rt.shape[-2] if Rt.dim() == 3 else None
+            if n_atoms is None:
+                raise ValueError('R must have shape [M, N, 3]')
+            R_desc, R_d_desc = desc_from_R_device(self.lib, self.ctx, Rt, n_atoms, self.device, self._stream())
+        self._R_desc = to_dev(R_desc)
+        self._R_d_desc = None if R_d_desc is None else to_dev(R_d_desc)
+        self.M, self.D = self._R_desc.shape
         self.N = n_atoms_from_dim_d(self.D)
-        assert R_d_desc.shape == (self.M, self.D, 3)
+        assert self._R_d_desc is None or tuple(self._R_d_desc.shape) == (self.M, self.D, 3)
         self.dim_i = 3 * self.N
         self.n = self.M * self.dim_i
         self.sig = float(sig)
@@ -81,16 +140,9 @@ class Engine(object):
         self.pt0, self.pt1 = shard_points(self.M, rank, world)
         self.n_local = (self.pt1 - self.pt0) * self.dim_i
         self.row0 = self.pt0 * self.dim_i
-        self.h2d_bytes = R_desc.nbytes + R_d_desc.nbytes + dperms.nbytes + aperms.nbytes
-
-        self._R_desc = torch.from_numpy(R_desc).to(self.device)
-        self._R_d_desc = torch.from_numpy(R_d_desc).to(self.device)
+        self.h2d_bytes += dperms.nbytes + aperms.nbytes
         self._dperms = torch.from_numpy(dperms).to(self.device)
         self._aperms = torch.from_numpy(aperms).to(self.device)
-
-        ctx = ctypes.c_void_p()
-        _lib.check(self.lib.mlffpc_create(ctypes.byref(ctx), self.device.index))
-        self.ctx = ctx
         if world > 1:
             if init_comm is None:
                 raise ValueError('world > 1 needs init_comm (see dist.init_engine_comm)')
@@ -260,6 +312,41 @@ class Engine(object):
                                                nb.value, self._stream()))
         return out
 
+    # ---- prediction (GDMLPredict.predict) --------------------------------------------------------
+    def desc_from_R(self, R):
+        """(R_desc[B, D], R_d_desc[B, D, 3]) on the device for geometries R[B, N, 3] / [B, 3N] (host or device)."""
+        return desc_from_R_device(self.lib, self.ctx, R, self.N, self.device, self._stream())
+
+    def d_desc_dot_vec(self, v):
+        """beta[M, D] = J_m v_m on the device (utils/desc.py:394-405; model['R_d_desc_alpha'], train.py:640-645)."""
+        assert v.numel() >= self.n and v.is_contiguous()
+        out = self.empty(self.M, self.D)
+        _lib.check(self.lib.mlffpc_d_desc_dot_vec(self.ctx, _ptr(v), _ptr(out), self._stream()))
+        return out
+
+    def predict(self, R_desc_q, R_d_desc_q, alphas=None, beta=None, want_E=True, max_batch=None):
+        """Unscaled (E[B], F[B, 3N]) of the query geometries for coefficients ``alphas`` (full n-vector on the device)
+        or ``beta[M, D] = J alpha`` (model['R_d_desc_alpha']); queries are processed in batches that keep the
+        [B, 2 M S] pair tables under ~4 GB."""
+        assert (alphas is None) != (beta is None), 'give exactly one of alphas and beta'
+        Bq = R_desc_q.shape[0]
+        F = self.empty(Bq, self.dim_i)
+        E = self.empty(Bq) if want_E else None
+        if max_batch is None:
+            max_batch = max(64, min(32768, int((4 << 30) // max(1, 16 * self.M * self.S))))
+        nb = ctypes.c_int64()
+        for s0 in range(0, Bq, max_batch):
+            b = min(max_batch, Bq - s0)
+            _lib.check(self.lib.mlffpc_predict_workspace_bytes(self.ctx, b, ctypes.byref(nb)))
+            ws = self._ws('predict', nb.value)
+            xd = R_desc_q[s0:s0 + b]
+            gd = R_d_desc_q[s0:s0 + b]
+            assert xd.is_contiguous() and gd.is_contiguous()
+            _lib.check(self.lib.mlffpc_predict(self.ctx, _ptr(xd), _ptr(gd), b, _ptr(alphas), _ptr(beta), _ptr(F[s0:s0 + b]),
+                                               _ptr(E[s0:s0 + b]) if want_E else ctypes.c_void_p(0), _ptr(ws), nb.value,
+                                               self._stream()))
+        return E, F
+
     # ---- dense ----------------------------------------------------------------------------
     def dgemm(self, A, B, trans_b=False, alpha=1.0, beta=0.0, out=None):
         m, k = A.shape
@@ -367,10 +454,14 @@ class Engine(object):
 
     # ---- PCG ------------------------------------------------------------------------------
     def pcg(self, b, lam, tol, maxiter, K_local=None, T=None, precon_sign=1.0, x0=None, want_hist=False, Mk=None,
-            E=None):
-        """Returns (x_local, iters, resid, info, bnrm2[, hist])."""
+            E=None, resume_iters=0, x_inout=None):
+        """Returns (x_local, iters, resid, info, bnrm2[, hist]).  ``resume_iters`` / ``x_inout``: continue the run a
+        previous call (same engine, nothing else run through ``pcg`` in between) stopped at its iteration cap."""
         k = 0 if T is None else T.shape[0]
-        x = torch.zeros(self.n_local, dtype=torch.float64, device=self.device) if x0 is None else x0.clone()
+        if x_inout is not None:
+            x = x_inout
+        else:
+            x = torch.zeros(self.n_local, dtype=torch.float64, device=self.device) if x0 is None else x0.clone()
         nb = ctypes.c_int64()
         _lib.check(self.lib.mlffpc_pcg_workspace_bytes(self.ctx, k, 1 if K_local is None else 0, ctypes.byref(nb)))
         ws = self._ws('pcg', nb.value)
@@ -381,7 +472,7 @@ class Engine(object):
         _lib.check(self.lib.mlffpc_pcg(
             self.ctx, _ptr(K_local), 0 if K_local is None else K_local.stride(0), float(lam), _ptr(T), k,
             0 if T is None else T.stride(0), float(precon_sign), _ptr(Mk), _ptr(E), _ptr(b), _ptr(x), float(tol),
-            int(maxiter), out,
+            int(maxiter), int(resume_iters), out,
             hist.ctypes.data_as(ctypes.c_void_p) if hist is not None else ctypes.c_void_p(0), _ptr(ws), nb.value,
             self._stream()))
         self.last_pcg_stats = {'op_ms': float(out[4]), 'op_calls': int(out[5]), 'precon_ms': float(out[6])}

@@ -45,6 +45,20 @@ class Iterative(object):
                              rank=rank, world=world, init_comm=init_engine_comm if world > 1 else None)
         return self.engine
 
+    def _sync_draw(self, idxs):
+        """Column draws come from numpy's global RNG like in the reference (iterative_solver.py:685, :709, :747, :472).
+        In a sharded run every rank draws (so the RNG streams advance alike) but rank 0's result is the one all ranks
+        use -- nothing guarantees that the ranks were seeded identically."""
+        eng = self.engine
+        if eng.world == 1:
+            return idxs
+        import torch.distributed as dist
+
+        dev = eng.device if dist.get_backend() == 'nccl' else torch.device('cpu')
+        t = torch.as_tensor(np.ascontiguousarray(idxs, dtype=np.int64), device=dev)
+        dist.broadcast(t, src=0)
+        return t.cpu().numpy()
+
     def _gather_kmm(self, Bt, idxs):
         """K_mm[a, b] = K[idxs[a], idxs[b]] from the transposed local panel Bt[b, r] = K[row0 + r, idxs[b]]."""
         eng = self.engine
@@ -105,7 +119,7 @@ class Iterative(object):
         n_train, dim_i = eng.M, eng.dim_i
         dim_m = np.maximum(1, n_inducing_pts // 4) * dim_i
         if idxs_ordered_by_lev_score is None:
-            lev_approx_idxs = np.sort(np.random.choice(n_train * dim_i, dim_m, replace=False))
+            lev_approx_idxs = self._sync_draw(np.sort(np.random.choice(n_train * dim_i, dim_m, replace=False)))
         else:
             assert len(idxs_ordered_by_lev_score) == n_train * dim_i
             lev_approx_idxs = np.sort(idxs_ordered_by_lev_score[-dim_m:])
@@ -144,7 +158,8 @@ class Iterative(object):
         return 'assembled_sym' if int(fits.item()) == 1 else 'matrix_free'
 
     # ------------------------------------------------------------------ device-resident solve
-    def solve_device(self, task, eng, y_t, break_percentage, str_preconditioner, n_inducing_pts, x0=None):
+    def solve_device(self, task, eng, y_t, break_percentage, str_preconditioner, n_inducing_pts, x0=None,
+                     on_segment=None):
         """Everything between the H2D of the inputs and the D2H of the solution: preconditioner build,
         kernel operator, PCG.  ``y_t`` is the full right-hand side on the device.  Returns
         ``(x_local, iters, resid, info, inducing_pts_idxs, info_cholesky, t_precon, t_cg)``."""
@@ -163,7 +178,7 @@ class Iterative(object):
         if str_preconditioner in NYSTROM_KEYS:
             k = int(break_percentage * n)
             if str_preconditioner == 'random_scores':
-                inducing_pts_idxs = np.sort(np.random.choice(np.arange(n), size=k, replace=False))
+                inducing_pts_idxs = self._sync_draw(np.sort(np.random.choice(np.arange(n), size=k, replace=False)))
             elif str_preconditioner in ['truncated_cholesky', 'truncated_cholesky_custom']:
                 k_truncate = task['truncated_cholesky']
                 k_truncate = k_truncate if k_truncate < k else k
@@ -172,7 +187,8 @@ class Iterative(object):
                 index_columns_cholesky = idx_t.cpu().numpy()
                 inducing_pts_cholesky = index_columns_cholesky[:k_truncate]
                 k_random = int(k - k_truncate) if k_truncate < k else 0
-                inducing_pts_random = np.random.choice(index_columns_cholesky[k_truncate:], size=k_random, replace=False)
+                inducing_pts_random = self._sync_draw(
+                    np.random.choice(index_columns_cholesky[k_truncate:], size=k_random, replace=False))
                 inducing_pts_idxs = np.sort(np.concatenate([inducing_pts_cholesky, inducing_pts_random]))
             else:  # 'lev_scores', 'inverse_lev', 'lev_random'
                 lev_scores, idxs_ordered = self._lev_scores(R_desc, R_d_desc, tril_perms_lin, sig, lam, False,
@@ -183,7 +199,7 @@ class Iterative(object):
                     inducing_pts_idxs = np.sort(idxs_ordered[-k:])
                 else:
                     p = lev_scores / lev_scores.sum()
-                    inducing_pts_idxs = np.sort(np.random.choice(np.arange(n), size=k, replace=False, p=p))
+                    inducing_pts_idxs = self._sync_draw(np.sort(np.random.choice(np.arange(n), size=k, replace=False, p=p)))
             assert inducing_pts_idxs.shape == (k,), 'Incorrect number of inducing points.'
             if str_preconditioner == 'truncated_cholesky_custom':
                 P_op = self._init_precon_operator_sb(task, R_desc, R_d_desc, tril_perms_lin, inducing_pts_idxs)
@@ -244,10 +260,34 @@ class Iterative(object):
 
         maxiter = int(task.get('_maxiter', 3 * n_atoms * n_train * 5))  # :1002 (5 n; '_maxiter' caps sweeps)
         tic_start = timeit.default_timer()
-        res = eng.pcg(
-            y_t[eng.row0:eng.row0 + eng.n_local].contiguous(), lam, task['solver_tol'], maxiter,
-            K_local=self.K_local, T=P_op.T, precon_sign=P_op.sign, x0=x0, want_hist=bool(task.get('_want_hist')),
-            Mk=P_op.Mk, E=P_op.E)
+        b_local = y_t[eng.row0:eng.row0 + eng.n_local].contiguous()
+        kw = dict(K_local=self.K_local, T=P_op.T, precon_sign=P_op.sign, want_hist=bool(task.get('_want_hist')),
+                  Mk=P_op.Mk, E=P_op.E)
+        if on_segment is None:
+            res = eng.pcg(b_local, lam, task['solver_tol'], maxiter, x0=x0, **kw)
+        else:
+            # One uninterrupted CG recurrence cut into segments: after each, the caller gets the current iterate (the
+            # reference writes an unconverged model every ~2 minutes from scipy's callback, iterative_solver.py:919-954).
+            period = float(task.get('_checkpoint_seconds', 120.0))
+            seg = int(task.get('_checkpoint_first_iters', 50))
+            done, x_io, hist0 = 0, None, None
+            while True:
+                cap = min(done + max(seg, 1), maxiter)
+                t_seg = timeit.default_timer()
+                res = eng.pcg(b_local, lam, task['solver_tol'], cap, x0=x0 if done == 0 else None,
+                              resume_iters=done, x_inout=x_io, **kw)
+                sync()
+                x_io, it_now, info_now = res[0], res[1], res[3]
+                if hist0 is None and kw['want_hist']:
+                    hist0 = res[5][0]
+                if info_now == 0 or it_now >= maxiter or it_now < cap:
+                    break
+                dt = max(timeit.default_timer() - t_seg, 1e-6)
+                seg = int(np.ceil(period * (it_now - done) / dt))
+                done = it_now
+                on_segment(x_io, done, res[2])
+            if kw['want_hist']:
+                res[5][0] = hist0
         x, iters, resid, info, bnrm2 = res[:5]
         if task.get('_want_hist'):
             self.timings['resid_hist_rel'] = res[5] / bnrm2
@@ -294,8 +334,33 @@ class Iterative(object):
             x0_full = torch.as_tensor(-np.asarray(alphas0_F, dtype=np.float64).ravel(), device=eng.device)
             x0 = x0_full[eng.row0:eng.row0 + eng.n_local].contiguous()
         sync()
+        on_segment = None
+        if save_progr_callback is not None:
+            def on_segment(x_local, iters_done, resid_now):
+                """Unconverged model for the caller (iterative_solver.py:919-954): current coefficients, iteration count
+                and -- when energies are trained -- the integration constant of the current iterate."""
+                alphas_now = (-allgather_rows(eng, x_local)).cpu().numpy()
+                gt = self.gdml_train
+                if gt is None or not hasattr(gt, 'create_model'):
+                    unconv = {'type': 'm', 'alphas_F': alphas_now, 'solver_iters': num_iters0 + iters_done + 1,
+                              'solver_resid': resid_now}
+                else:
+                    extra = {'engine': eng} if getattr(gt, '_mlffpc_native', False) else {}  # the reference's has no such kwarg
+                    unconv = gt.create_model(task, 'cg', R_desc, R_d_desc, tril_perms_lin, y_std, alphas_now,
+                                             solver_resid=resid_now, solver_iters=num_iters0 + iters_done + 1,
+                                             norm_y_train=np.linalg.norm(y), inducing_pts_idxs=None, **extra)
+                    if task.get('E_train') is not None and task.get('use_E', False):
+                        a_dev = torch.as_tensor(np.ascontiguousarray(alphas_now), device=eng.device)
+                        E_raw, _ = eng.predict(eng._R_desc, eng._R_d_desc, alphas=a_dev, want_E=True)
+                        E_pred = E_raw.cpu().numpy() * y_std
+                        E_ref = np.squeeze(task['E_train'])
+                        unconv['c'] = np.sum(E_ref - E_pred) / E_ref.shape[0]
+                if eng.rank == 0:
+                    save_progr_callback(unconv)
+
         (x, iters, resid, info, inducing_pts_idxs, info_cholesky, total_time_preconditioner,
-         total_time_cg) = self.solve_device(task, eng, y_t, break_percentage, str_preconditioner, n_inducing_pts, x0)
+         total_time_cg) = self.solve_device(task, eng, y_t, break_percentage, str_preconditioner, n_inducing_pts, x0,
+                                            on_segment=on_segment)
         total_time_cholesky = total_time_preconditioner
         k_rank = self.timings['k']
 

@@ -226,6 +226,56 @@ def kernel_matvec_torch_cpu(Rs_t, Xp_t, R_d_desc, tril_perms_lin, sig, v, batch=
     return torch.cat(out).numpy().reshape(-1)
 
 
+def desc_from_R(R):
+    """``(R_desc[M, D], R_d_desc[M, D, 3])`` for geometries ``R[M, N, 3]``: ``x_d = 1/|r_a - r_b|``,
+    ``g_d = (r_a - r_b)/|r_a - r_b|^3`` over the lower-triangle pairs (utils/desc.py:112-200, :292-358)."""
+    R = np.asarray(R, dtype=float)
+    n_atoms = R.shape[1]
+    a, b = np.tril_indices(n_atoms, k=-1)
+    pdiff = R[:, a, :] - R[:, b, :]
+    pdist = np.sqrt(np.einsum('mdc,mdc->md', pdiff, pdiff))
+    return 1.0 / pdist, pdiff / (pdist ** 3)[..., None]
+
+
+def predict(R_desc_train, R_d_desc_alpha, tril_perms_lin, sig, std, c, Rq):
+    """Energies and forces of query geometries ``Rq[B, N, 3]`` from a model (``GDMLPredict.predict``,
+    predict.py:997-1110; worker :72-234).  With ``beta = R_d_desc_alpha`` (= J alpha, train.py:640-645), per query::
+
+        diff = x_q - x_j^(p);  rho = sqrt5 |diff|;  m = 5/(3 sig^3) exp(-rho/sig);  a = diff . beta_j^(p)
+        F_desc = 5/sig sum_jp (a m) diff - sum_jp m (rho + sig) beta_j^(p);   E = sum_jp a m (rho + sig)
+        E <- E std + c;   F = (J_q^T F_desc) std
+    """
+    M, D = R_desc_train.shape
+    xq, gq = desc_from_R(Rq)
+    Xp = permuted_rows(R_desc_train, tril_perms_lin).reshape(-1, D)
+    Bp = permuted_rows(np.asarray(R_d_desc_alpha), tril_perms_lin).reshape(-1, D)
+    sqrt5 = np.sqrt(5.0)
+    E = np.zeros(xq.shape[0])
+    Fd = np.zeros_like(xq)
+    for i in range(xq.shape[0]):
+        diff = xq[i][None, :] - Xp
+        rho = sqrt5 * np.linalg.norm(diff, axis=1)
+        m = 5.0 / (3 * sig ** 3) * np.exp(-rho / sig)
+        a = np.einsum('ji,ji->j', diff, Bp)
+        Fd[i] = (a * m).dot(diff) * (5.0 / sig)
+        m2 = m * (rho + sig)
+        Fd[i] -= m2.dot(Bp)
+        E[i] = a.dot(m2)
+    F = vec_dot_d_desc(gq, Fd)
+    return E * std + c, F * std
+
+
+def recov_int_const(E_pred, E_ref):
+    """Least-squares integration constant with the reference's label checks (train.py:1036-1119): ``None`` when the
+    labels look like gradients, are uncorrelated with the prediction or live on a different scale."""
+    E_ref = np.squeeze(E_ref)
+    e_fact = np.linalg.lstsq(np.column_stack((E_pred, np.ones(E_ref.shape))), E_ref, rcond=-1)[0][0]
+    corrcoef = np.corrcoef(E_ref, E_pred)[0, 1]
+    if np.sign(e_fact) == -1 or corrcoef < 0.95 or np.abs(e_fact - 1) > 1e-1:
+        return None
+    return np.sum(E_ref - E_pred) / E_ref.shape[0]
+
+
 def kernel_operator(R_desc, R_d_desc, tril_perms_lin, sig, lam):
     """``v -> K v - lam v``  (iterative_solver.py:438-443).  CG is run on its negative."""
 

@@ -239,7 +239,44 @@ def case_cfg1_solve(name='cfg1_nanotube_m9', frac_k=None):
     print('wrote', name, 'n =', n, 'k =', k, 'iters', num_iters, 'resid %.3e' % resid, 'conv', is_conv)
 
 
+def case_predict(name, kind, M, perms, seed, n_query=17, frac=0.2, tol=1e-6):
+    """Reference ``GDMLTrain.train`` (model dict incl. R_d_desc_alpha and the integration constant of
+    ``_recov_int_const``, train.py:597-702, :972-1119) followed by ``GDMLPredict.predict`` on geometries that are not
+    in the training set, both CPU routes of the reference (numpy worker predict.py:72-234 and the torch module
+    torchtools.py:172-272)."""
+    from sgdml.predict import GDMLPredict
+
+    ds = synthetic.make_dataset(kind, M + n_query, seed=seed)
+    task = ref_shims.make_task(sgdml, ds, M, perms, sig=SIG, solver_tol=tol)
+    np.random.seed(0)
+    model = GT.train(task, callback=noop, break_percentage=frac, str_preconditioner='cholesky')
+    assert model['is_conv']
+    Rq = ds['R'][M:M + n_query].reshape(n_query, -1)
+    E_np, F_np = GDMLPredict(model, use_torch=False).predict(Rq)
+    E_t, F_t = GDMLPredict(model, use_torch=True).predict(Rq)
+    assert np.abs(E_np - E_t).max() < 1e-9 * np.abs(E_np).max() and np.abs(F_np - F_t).max() < 1e-9 * np.abs(F_np).max()
+    # training-mode prediction (descriptors given), as _recov_int_const uses it
+    N = ds['R'].shape[1]
+    desc = Desc(N, max_processes=1)
+    Rtr = task['R_train'].reshape(M, -1)
+    R_desc, R_d_desc = desc.from_R(Rtr, callback=noop)
+    E_tr, F_tr = GDMLPredict(model, use_torch=False).predict(Rtr, R_desc, R_d_desc)
+    out = dict(kind=kind, M=M, N=N, perms=perms, seed=seed, sig=SIG, frac=frac, tol=tol,
+               R_train=task['R_train'], F_train=task['F_train'], E_train=task['E_train'], z=ds['z'],
+               alphas_F=model['alphas_F'], R_d_desc_alpha=model['R_d_desc_alpha'], R_desc_T=model['R_desc'],
+               tril_perms_lin=model['tril_perms_lin'], c=model['c'], std=model['std'], lam=model['lam'],
+               solver_iters=model['solver_iters'], use_E=model['use_E'],
+               R_query=Rq, E_query=E_np, F_query=F_np, E_train_pred=E_tr, F_train_pred=F_tr,
+               model_keys=np.array(sorted(model.keys())))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print('wrote', name, 'iters', model['solver_iters'], 'c', model['c'], 'use_E', model['use_E'])
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'predict':
+        case_predict('predict_eth_s6_m24', 'ethanol', 24, synthetic.ethanol_perms(), seed=6)
+        case_predict('predict_asp_s1_m10', 'aspirin', 10, np.arange(21)[None], seed=7)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'cfg1':
         case_cfg1_solve()
         sys.exit(0)

@@ -54,9 +54,12 @@ def _run_both(system, lam, tol, maxiter, precon, x0=None, mode='assembled'):
 
 
 @pytest.mark.parametrize('mode', ['assembled', 'assembled_sym', 'matrix_free'])
-@pytest.mark.parametrize('precon', [False, True])
-def test_step_for_step_agreement(system, mode, precon):
-    (x, it, resid, info, hist), (x_ref, it_ref, res_ref, info_ref) = _run_both(system, 1e-2, 1e-8, 5000, precon, mode=mode)
+@pytest.mark.parametrize('precon,lam', [(False, 1.0), (True, 1e-2), (True, 1e-5)])
+def test_step_for_step_agreement(system, mode, precon, lam):
+    """Well-conditioned cases where rounding cannot move the count: -K + I without a preconditioner (condition number
+    ~2; with lam = 1e-2 the six-fold eigenvalue lam of the rigid-body null space of K makes the unpreconditioned count
+    depend on the summation order: 27/28 on the device, 30 in numpy), and the preconditioned solves."""
+    (x, it, resid, info, hist), (x_ref, it_ref, res_ref, info_ref) = _run_both(system, lam, 1e-8, 5000, precon, mode=mode)
     assert info == 0 and info_ref == 0
     assert it == it_ref, (it, it_ref)
     assert relerr(x, x_ref) < 1e-9
