@@ -296,6 +296,85 @@ def workload_config(inp, args, world):
                             16.0 * inp['k'] * inp['n'] / world / 1e9)}
 
 
+# ----------------------------------------------------------------------------- north-star systems (8 GPUs)
+FP64_DGEMM_TFLOPS_MEASURED = 35.5   # cuBLAS DGEMM 8192^3 on this pool's B200 (profiles/r01t_fp64_peak_16w.json)
+
+
+def north_star_solve(workload, mode, form, k, tol, maxiter, world, rank, dev, hbm_peak, timed_steps=1, warm_steps=0):
+    """One of BASELINE.json's multi-GPU configurations end to end on the device (inputs resident in HBM): preconditioner
+    build, operator set-up, PCG.  Returns a dict for the JSON line (rank 0 prints it)."""
+    import torch
+    import torch.distributed as dist
+
+    from mlff_preconditioner_b200.dist import init_engine_comm, symop_entries_read, symop_plan
+    from mlff_preconditioner_b200.engine import Engine
+    from mlff_preconditioner_b200.solvers.iterative_solver import Iterative
+
+    inp = make_inputs(workload, tol_override=tol, k_override=k)
+    n, k = inp['n'], inp['k']
+    frac = (k + 0.5) / n
+    task = dict(inp['task'])
+    task.update(kernel_mode=mode, precon_form=form, _want_hist=True, _maxiter=int(maxiter), solver_tol=tol)
+    eng = Engine(inp['R_desc'], inp['R_d_desc'], inp['tpl'], 10, perms=inp['perms'], rank=rank, world=world,
+                 init_comm=init_engine_comm if world > 1 else None)
+    y_t = torch.as_tensor(inp['y'], device=dev)
+    if mode == 'assembled_sym':
+        task['_K_buffer'] = eng.empty(eng.symop_storage_elems())
+    n_ind = min(inp['M'], int(max(np.ceil(frac * inp['M']), 1)))
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm_steps):
+        Iterative(None, None).solve_device(task, eng, y_t, frac, 'cholesky', n_ind)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(timed_steps):
+        it = Iterative(None, None)
+        out = it.solve_device(task, eng, y_t, frac, 'cholesky', n_ind)
+    e1.record()
+    sync_all()
+    secs = e0.elapsed_time(e1) * 1e-3 / timed_steps
+    if world > 1:
+        t = torch.tensor([secs], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    tm = it.timings
+    st = tm['pcg_stats']
+    op_s = st['op_ms'] * 1e-3 / max(st['op_calls'], 1)
+    res = {'workload': workload, 'n': n, 'k': k, 'tol': tol, 'kernel_mode': mode, 'precon_form': form, 'n_gpus': world,
+           'value': secs, 'unit': 's', 'steps': timed_steps, 'cg_iters': int(out[1]), 'converged': out[3] == 0,
+           'rel_resid': float(out[2] / np.linalg.norm(inp['y'])),
+           'phases': {'preconditioner_s': tm['preconditioner'], 'pchol_build_s': tm.get('pchol_build'),
+                      'assemble_s': tm['assemble'], 'cg_s': tm['cg'], 'operator_avg_ms': op_s * 1e3,
+                      'precon_apply_avg_ms': st['precon_ms'] / max(st['op_calls'], 1),
+                      'rel_resid_every_200_iters': [float('%.3g' % v) for v in tm['resid_hist_rel'][::200]]}}
+    if mode == 'assembled_sym':
+        entries = symop_entries_read(symop_plan(eng.M, world, rank), eng.dim_i)
+        gbs = (8.0 * entries + 8.0 * eng.n + 8.0 * eng.n_local) / op_s / 1e9
+        res['roofline'] = {'bound': 'hbm', 'kernel': 'symv_tma_kernel (+ reduce, + reduce-scatter of the partial products)',
+                           'achieved_per_gpu': gbs, 'peak_per_gpu': hbm_peak, 'frac': gbs / hbm_peak,
+                           'achieved_aggregate': gbs * world, 'peak_aggregate': hbm_peak * world, 'unit': 'GB/s',
+                           'frac_of_nominal_8TBs': gbs / 8000.0,
+                           'equivalent_full_gemv_aggregate': 8.0 * eng.n * eng.n / op_s / 1e9,
+                           'note': 'rank 0; symmetric tile storage, every stored entry read once per matvec'}
+    else:
+        flops = 8.0 * (eng.pt1 - eng.pt0) * eng.M * eng.S * eng.D
+        tf = flops / op_s / 1e12
+        res['roofline'] = {'bound': 'fp64', 'kernel': 'matvec_free (pairs + DMMA GEMM)', 'achieved_per_gpu': tf,
+                           'peak_per_gpu': FP64_DGEMM_TFLOPS_MEASURED, 'frac': tf / FP64_DGEMM_TFLOPS_MEASURED,
+                           'achieved_aggregate': tf * world, 'unit': 'TFLOP/s',
+                           'peak_source': 'cuBLAS DGEMM measured on this pool (profiles/r01t_fp64_peak_16w.json)',
+                           'apply_share_of_iteration': st['precon_ms'] / max(st['precon_ms'] + st['op_ms'], 1e-9)}
+    eng.close()
+    del eng, it, out, task
+    torch.cuda.empty_cache()
+    return res
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     # rank 0 prints exactly ONE line on stdout: anything native libraries write to fd 1 (NCCL banners) goes to stderr
@@ -426,9 +505,12 @@ def run_ours(args):
                                                    8.0 * eng.n_local * eng.n / avg_op_s / 1e9)}
     else:
         flops = 8.0 * (eng.pt1 - eng.pt0) * eng.M * eng.S * eng.D
-        roofline = {'bound': 'fp64', 'kernel': 'matvec_free (pairs + DMMA GEMM)', 'achieved': flops / avg_op_s / 1e12,
-                    'peak': 40.0, 'unit': 'TFLOP/s', 'frac': flops / avg_op_s / 1e12 / 40.0, 'traffic': None,
-                    'peak_source': 'nominal B200 fp64 (no measured fp64 peak in MEASURED_PEAKS.json)',
+        tf = flops / avg_op_s / 1e12
+        roofline = {'bound': 'fp64', 'kernel': 'matvec_free (pairs + DMMA GEMM)', 'achieved': tf,
+                    'peak': FP64_DGEMM_TFLOPS_MEASURED, 'unit': 'TFLOP/s', 'frac': tf / FP64_DGEMM_TFLOPS_MEASURED,
+                    'traffic': None,
+                    'peak_source': 'cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01t_fp64_peak_16w.json); '
+                                   'MEASURED_PEAKS.json has no fp64 entry, nominal B200 fp64 is 40 TFLOP/s',
                     'avg_launch_ms': avg_op_s * 1e3, 'launches_timed': op_calls}
     # measured DRAM traffic of the dominant kernel (ncu --set full), only valid for the configuration it was captured on
     if args.workload == 'cfg2' and world == 1 and not args.M:
@@ -515,6 +597,29 @@ def run_ours(args):
             'value': total, 'unit': 's', 'cores': os.cpu_count(), 'kind': 'port', 'extrapolated': True,
             'sample': '%s; cg_iters=%d from %s' % (CPU_SAMPLE_TEXT, ref_iters, ref_src),
             'detail': detail, 'measured_full_solves': measured_cpu_points(args.workload)}
+    # ---- BASELINE.json's multi-GPU systems in front of the driver: cfg4 (n = 270 000 assembled) and cfg5 (n = 1.26 M
+    # matrix-free), one end-to-end solve each; `value` above stays on cfg2 so the strong-scaling curve is comparable
+    want_ns = args.north_star == 'on' or (args.north_star == 'auto' and world == 8 and args.workload == 'cfg2')
+    if want_ns:
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+        ns = {}
+        try:
+            ns['cfg4'] = north_star_solve('cfg4', 'assembled_sym', args.precon_form if args.precon_form != 'reorth' else 'projected',
+                                          None, 1e-6, 100000, world, rank, dev, peak, timed_steps=1, warm_steps=1)
+        except Exception as exc:  # noqa: BLE001  (every rank fails alike: sizes are deterministic)
+            ns['cfg4'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
+        try:
+            ns['cfg5'] = north_star_solve('cfg5', 'matrix_free', 'projected', args.ns_cfg5_k, args.ns_cfg5_tol,
+                                          args.ns_cfg5_maxiter, world, rank, dev, peak)
+            ns['cfg5']['note'] = ('k = %d (%.1f %% of n) instead of the rule-of-thumb 46 702: at that rank each GPU would hold '
+                                  '58.8 GB of factor and the replicated k^3 factorisation would dominate the solve; tol = %g is '
+                                  "the reference's own solver_tol for its n = 5e5 runs (create_data.py:88-97)"
+                                  % (args.ns_cfg5_k, 100.0 * args.ns_cfg5_k / 1260000, args.ns_cfg5_tol))
+        except Exception as exc:  # noqa: BLE001
+            ns['cfg5'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
+        line['north_star'] = ns
     if rank == 0:
         real_stdout.write(json.dumps(line) + '\n')
         real_stdout.flush()
@@ -542,6 +647,12 @@ def main():
     ap.add_argument('--precon-form', default='projected', choices=['projected', 'woodbury', 'orthonormal', 'reorth'],
                     help="evaluation of the pivoted-Cholesky preconditioner (L L^T + lam I)^-1: 'projected' (benchmark "
                          "default), 'woodbury' (the reference's formula, the library default), 'orthonormal', 'reorth'")
+    ap.add_argument('--north-star', default='auto', choices=['auto', 'on', 'off'],
+                    help="add one end-to-end solve of cfg4 (n = 270 000, assembled) and cfg5 (n = 1.26 M, matrix-free) to the "
+                         "JSON line; 'auto' = when running cfg2 on 8 GPUs")
+    ap.add_argument('--ns-cfg5-k', type=int, default=16384)
+    ap.add_argument('--ns-cfg5-tol', type=float, default=1e-4)
+    ap.add_argument('--ns-cfg5-maxiter', type=int, default=10000)
     ap.add_argument('--opt', action='append', default=[], help='library option name=int (mlffpc_set_option), repeatable')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -25,6 +25,16 @@ struct ProfWindow {
 };
 ProfWindow prof_window(const char* phase);
 
+// MLFFPC_TIMING=1: the factorisation entry points synchronise after every sub-step and print its wall time to stderr
+// (development aid; unset = no synchronisation, no output)
+struct PhaseTimer {
+    cudaStream_t s;
+    bool on;
+    double t0;
+    explicit PhaseTimer(cudaStream_t stream);
+    void lap(const char* label);
+};
+
 #define MLFFPC_CUDA(call)                                                          \
     do {                                                                           \
         cudaError_t _e = (call);                                                   \

@@ -15,6 +15,8 @@
 // built (m - m0 <= a few dozen rows of Lt); when it is not, the panel is rebuilt from the current top
 // LA_C residual diagonals (which contain the arg-max by construction).  Same pivots, same factor up to
 // summation order; the HBM stream drops from 4 n k^2 bytes to about 4 n k^2 / (average run length).
+#include <string.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -346,6 +348,159 @@ __global__ void pchol_gather_cand_rows_kernel(const double* __restrict__ Lt, int
     Lc[(int64_t)j * ld_lc + t] = (owner && t < m) ? Lt[t * ld + (g - row0)] : 0.0;
 }
 
+// ---- host-free stepping of the look-ahead build ---------------------------------------------------------------
+// A step is two launches and (sharded) one collective, and the host does not wait for it:
+//   prepare (1 CTA)  apply the previous step's swap to index_columns / pos, reduce the candidate partials to this rank's
+//                    best row, and put {candidate, its factor row L[cand, m0:m]} into the send buffer
+//   allgather        LA_MSG doubles per rank (replaces the 32-byte allgather + the allreduce of the pivot row)
+//   update           every CTA picks the winner among the ranks' candidates; if its column is in the panel it runs the
+//                    Schur update for the factor columns m0 .. m-1, else (a miss, or a pivot <= 0) it sets `stalled`
+//                    and every later launch returns at once until the host has rebuilt the panel.
+// The host launches LA_CHUNK steps, then reads the 64-byte state once.
+constexpr int LA_MSG = 4 + LA_C;   // candidate (val, pos, idx, pad) + at most LA_C entries of its factor row
+constexpr int LA_CHUNK = 8;
+
+struct LaState {
+    int stalled;        // 1: a step could not run (panel miss or non-PSD pivot); cleared by the host
+    int flag;           // != 0: pivot <= 0 at step flag - 1 (incomplete_cholesky.py:62)
+    int slot;           // scratch of the merge kernel
+    int pad0;
+    long long stall_m;  // the step that stalled
+    long long miss_pi;  // its pivot row (input of the panel rebuild)
+    long long pend_m;   // swap of step pend_m (pivot pend_pi) not yet applied to index_columns / pos; -1: none
+    long long pend_pi;
+    long long done_m;   // steps completed
+    long long pad1;
+};
+
+__device__ __forceinline__ void la_apply_pending(LaState* st, int64_t* index_columns, int32_t* pos) {
+    if (st->pend_m >= 0) {
+        const int64_t mp = st->pend_m, pi = st->pend_pi;
+        const int32_t i_argmax = pos[pi];
+        const int64_t e = index_columns[mp];
+        index_columns[mp] = pi;
+        index_columns[i_argmax] = e;
+        pos[pi] = (int32_t)mp;
+        pos[e] = i_argmax;
+        st->pend_m = -1;
+    }
+}
+
+__global__ void pchol_la_prepare_kernel(const Cand* __restrict__ partials, int count, const double* __restrict__ Lt,
+                                        int64_t ld, int64_t m0, int64_t m, int64_t row0, int64_t* index_columns,
+                                        int32_t* pos, LaState* st, double* __restrict__ send) {
+    if (st->stalled) return;
+    __shared__ Cand sm[40];
+    if (threadIdx.x == 0) la_apply_pending(st, index_columns, pos);
+    double v = -1e300, p = 1e300, i = -1.0;
+    for (int t = threadIdx.x; t < count; t += blockDim.x) {
+        const Cand c = partials[t];
+        if (cand_better(c.val, c.pos, v, p)) { v = c.val; p = c.pos; i = c.idx; }
+    }
+    block_argmax(v, p, i, sm);
+    const Cand best = sm[0];
+    if (threadIdx.x == 0) { send[0] = best.val; send[1] = best.pos; send[2] = best.idx; send[3] = 0.0; }
+    const int64_t g = (int64_t)best.idx;
+    for (int64_t t = m0 + threadIdx.x; t < m; t += blockDim.x)
+        send[4 + (t - m0)] = (g >= 0) ? Lt[t * ld + (g - row0)] : 0.0;
+}
+
+__global__ void pchol_la_flush_kernel(LaState* st, int64_t* index_columns, int32_t* pos) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) la_apply_pending(st, index_columns, pos);
+}
+
+template <int MSPLIT>
+__global__ void __launch_bounds__(PCHOL_THREADS)
+pchol_la_update_kernel(double* __restrict__ Lt, int64_t ld, int64_t m0, int64_t m, int64_t n_local, int64_t row0,
+                       const double* __restrict__ panel, int64_t ld_panel, const double* __restrict__ gathered, int world,
+                       const int32_t* __restrict__ cslot, double* __restrict__ diag, const int32_t* __restrict__ pos,
+                       const int64_t* __restrict__ index_columns, Cand* partials, LaState* st) {
+    constexpr int COLS = PCHOL_THREADS / MSPLIT;
+    __shared__ double red[MSPLIT][COLS];
+    __shared__ Cand sm[40];
+    __shared__ double lrow[LA_C];
+    __shared__ double s_val;
+    __shared__ long long s_pi;
+    __shared__ int s_slot, s_rank, s_stalled;
+    if (threadIdx.x == 0) {
+        s_stalled = st->stalled;
+        double v = -1e300, p = 1e300, i = -1.0;
+        int wr = 0;
+        for (int r = 0; r < world; ++r) {
+            const double* c = gathered + (int64_t)r * LA_MSG;
+            if (cand_better(c[0], c[1], v, p)) { v = c[0]; p = c[1]; i = c[2]; wr = r; }
+        }
+        s_val = v; s_pi = (long long)i; s_rank = wr;
+        s_slot = (i >= 0.0) ? cslot[(int64_t)i] : -1;
+    }
+    __syncthreads();
+    if (s_stalled) return;
+    const int64_t pi = s_pi;
+    if (s_slot < 0 || !(s_val > 0.0)) {  // panel miss / non-PSD pivot: nothing is modified, the host takes over
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            st->stall_m = m;
+            st->miss_pi = pi;
+            if (!(s_val > 0.0) && st->flag == 0) st->flag = (int)(m + 1);
+            __threadfence();
+            st->stalled = 1;
+        }
+        return;
+    }
+    for (int t = threadIdx.x; t < (int)(m - m0); t += blockDim.x) lrow[t] = gathered[(int64_t)s_rank * LA_MSG + 4 + t];
+    __syncthreads();
+    const double piv = sqrt(s_val);
+    const int tc = threadIdx.x % COLS, ts = threadIdx.x / COLS;
+    const int64_t r = (int64_t)blockIdx.x * COLS + tc;
+    double acc = 0.0;
+    if (r < n_local) {
+        const double* Lp = Lt + r;
+        int64_t q = m0 + ts;
+        for (; q + 7 * MSPLIT < m; q += 8 * MSPLIT) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldcs(Lp + (q + u * MSPLIT) * ld);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = fma(t[u], lrow[q + u * MSPLIT - m0], acc);
+        }
+        for (; q < m; q += MSPLIT) acc = fma(__ldcs(Lp + q * ld), lrow[q - m0], acc);
+    }
+    if (MSPLIT > 1) {
+        red[ts][tc] = acc;
+        __syncthreads();
+        if (ts == 0) {
+#pragma unroll
+            for (int s2 = 1; s2 < MSPLIT; ++s2) acc += red[s2][tc];
+        }
+    }
+    double v = -1e300, p = 1e300, i = -1.0;
+    if (ts == 0 && r < n_local) {
+        const int64_t g = row0 + r;
+        // positions after this step's swap (applied to the arrays by the next prepare kernel): the pivot goes to m,
+        // the row that sat at m goes to where the pivot was
+        const int64_t e = index_columns[m];
+        int32_t ps = pos[g];
+        if (g == e && g != pi) ps = pos[pi];
+        double l;
+        if (g == pi) {
+            l = piv;
+        } else if (ps > m) {  // still a candidate row: i_pi = index_columns[m+1:]
+            const double* cp = panel + (int64_t)s_slot * ld_panel;
+            l = (cp[r] - acc) / piv;
+            const double dn = diag[r] - l * l;
+            diag[r] = dn;
+            v = dn; p = (double)ps; i = (double)g;
+        } else {
+            l = 0.0;
+        }
+        Lt[m * ld + r] = l;
+    }
+    block_argmax(v, p, i, sm);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = sm[0];
+        if (blockIdx.x == 0) { st->pend_m = m; st->pend_pi = pi; st->done_m = m + 1; }
+    }
+}
+
 static int pchol_msplit(int64_t n_local, int64_t m, int num_sms) {
     const int64_t want = (int64_t)num_sms * 1024;
     if (n_local >= want || m < 64) return 1;
@@ -355,7 +510,7 @@ static int pchol_msplit(int64_t n_local, int64_t m, int num_sms) {
 
 struct PcholWs {
     int64_t off_col, off_lrow, off_pos, off_cands, off_gathered, off_piv, off_cand_idx, off_cslot, off_panel, off_lc,
-        off_list, off_lists, total;
+        off_list, off_lists, off_state, off_send, off_recv, total;
 };
 static bool pchol_lookahead_enabled(const mlffpc_ctx* c, int64_t k, bool forced) {
     return c->pchol_lookahead && !forced && k >= 128 && (int64_t)c->comm.world * LA_LCAP <= LA_MAXE &&
@@ -379,6 +534,9 @@ static PcholWs pchol_layout(const mlffpc_ctx* c, int64_t k) {
     w.off_lc = o;       o = up(o + (la ? (int64_t)LA_C * (k + 2) * 8 : 0));
     w.off_list = o;     o = up(o + (la ? LA_LCAP * (int64_t)sizeof(Cand) : 0));
     w.off_lists = o;    o = up(o + (la ? (int64_t)c->comm.world * LA_LCAP * (int64_t)sizeof(Cand) : 0));
+    w.off_state = o;    o = up(o + 256);
+    w.off_send = o;     o = up(o + LA_MSG * 8);
+    w.off_recv = o;     o = up(o + (int64_t)c->comm.world * LA_MSG * 8);
     w.total = o + 256;
     return w;
 }
@@ -454,7 +612,86 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
     int64_t m0 = 0;        // factor columns already folded into the candidate panel
     int64_t refills = 0;
     ProfWindow pw = prof_window("pchol");
-    for (int64_t m = 0; m < k && status == MLFFPC_OK; ++m) {
+    int h_flag_la = 0;
+    if (la && k > 0) {
+        // ---- look-ahead build, host-free stepping (kernels above) ----------------------------------------------
+        LaState* st = (LaState*)(base + w.off_state);
+        double* send = (double*)(base + w.off_send);
+        double* recv = (world > 1) ? (double*)(base + w.off_recv) : send;
+        LaState* h_st = (LaState*)(ctx->h_scal + 24);  // pinned; 64 bytes
+        do {
+            LaState init;
+            memset(&init, 0, sizeof(init));
+            init.pend_m = -1;
+            *h_st = init;
+            cudaError_t e = cudaMemcpyAsync(st, h_st, sizeof(LaState), cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { status = cuda_fail(e, "pchol state init", __FILE__, __LINE__); break; }
+            if (n_part > MLFFPC_MAX_PARTIALS) { set_error("pchol_build: n_local too large (%lld rows)", (long long)nl); status = MLFFPC_ERR_INVALID; break; }
+            pchol_scan_kernel<<<(unsigned)n_part, 256, 0, s>>>(diag, nl, row0, pos, 0, partials);
+            ++g_launches;
+            prev_parts = (int)n_part;
+            // m0 = 0 with an empty panel: the first step misses by construction and builds the first panel
+            int64_t m = 0;
+            while (m < k && status == MLFFPC_OK) {
+                const int64_t chunk_end = (m + LA_CHUNK < k) ? (m + LA_CHUNK) : k;
+                for (int64_t mm = m; mm < chunk_end; ++mm) {
+                    pw.step(mm);
+                    pchol_la_prepare_kernel<<<1, 256, 0, s>>>(partials, prev_parts, Lt, ld, m0, mm, row0, index_columns, pos, st, send);
+                    if (world > 1) {
+                        status = comm_allgather(ctx->comm, send, recv, LA_MSG * sizeof(double), s);
+                        if (status != MLFFPC_OK) break;
+                    }
+                    // One thread per row, always: a step applies at most LA_C factor columns, and the candidate partials
+                    // must keep ONE layout -- a stalled (no-op) launch leaves the previous step's partials in place.
+                    pchol_la_update_kernel<1><<<(unsigned)n_part, PCHOL_THREADS, 0, s>>>(Lt, ld, m0, mm, nl, row0, panel, nl, recv, world, cslot, diag, pos, index_columns, partials, st);
+                    g_launches += 2;
+                    if (step_ms_host) cudaEventRecord(ev[(size_t)mm + 1], s);
+                }
+                if (status != MLFFPC_OK) break;
+                cudaError_t e2 = cudaMemcpyAsync(h_st, st, sizeof(LaState), cudaMemcpyDeviceToHost, s);
+                if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s);
+                if (e2 == cudaSuccess) e2 = cudaGetLastError();
+                if (e2 != cudaSuccess) { status = cuda_fail(e2, "pchol chunk", __FILE__, __LINE__); break; }
+                if (h_st->flag != 0) { h_flag_la = h_st->flag; break; }
+                if (!h_st->stalled) { m = chunk_end; continue; }
+                // (2b) panel rebuild at the stalled step: top rows by residual diagonal -> merged candidate list ->
+                // columns of A -> fold in L[:, :m]
+                m = h_st->stall_m;
+                ++refills;
+                pchol_topc_kernel<<<1, 1024, 0, s>>>(diag, nl, row0, pos, m, LA_C, my_list);
+                status = comm_allgather(ctx->comm, my_list, all_lists, LA_LCAP * sizeof(Cand), s);
+                if (status != MLFFPC_OK) break;
+                int E = 1;
+                while (E < world * LA_LCAP) E <<= 1;
+                pchol_merge_kernel<<<1, 1024, 3 * E * sizeof(double), s>>>(all_lists, world * LA_LCAP, (const int64_t*)&st->miss_pi,
+                                                                         cand_idx, cslot, &st->slot);
+                g_launches += 2;
+                status = mlffpc_kernel_columns(ctx, cand_idx, LA_C, panel, nl, -1.0, nullptr, 0, (void*)s);
+                if (status != MLFFPC_OK) break;
+                if (m > 0) {
+                    const int64_t ld_lc = (m + 1) & ~(int64_t)1;  // even pitch: the GEMM stages 16-byte copies
+                    pchol_gather_cand_rows_kernel<<<dim3((unsigned)((ld_lc + 255) / 256), LA_C), 256, 0, s>>>(
+                        Lt, ld, m, ld_lc, cand_idx, row0, nl, Lc);
+                    ++g_launches;
+                    status = comm_allreduce_sum(ctx->comm, Lc, (size_t)(LA_C * ld_lc), s);
+                    if (status != MLFFPC_OK) break;
+                    status = dgemm(false, LA_C, nl, m, -1.0, Lc, ld_lc, Lt, ld, 1.0, panel, nl, false, s);
+                    if (status != MLFFPC_OK) break;
+                }
+                m0 = m;
+                e2 = cudaMemsetAsync(&st->stalled, 0, sizeof(int), s);
+                if (e2 != cudaSuccess) { status = cuda_fail(e2, "pchol clear stall", __FILE__, __LINE__); break; }
+            }
+            if (status == MLFFPC_OK && h_flag_la == 0) {
+                pchol_la_flush_kernel<<<1, 32, 0, s>>>(st, index_columns, pos);
+                ++g_launches;
+                const cudaError_t e3 = cudaStreamSynchronize(s);
+                if (e3 != cudaSuccess) status = cuda_fail(e3, "pchol end", __FILE__, __LINE__);
+            }
+        } while (0);
+    }
+    for (int64_t m = 0; !la && m < k && status == MLFFPC_OK; ++m) {
         pw.step(m);
         // (1) candidates -> this rank's best
         if (m == 0) {
@@ -549,8 +786,8 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
     ctx->last_pchol_refills = refills;
 
     pw.end();
-    int h_flag = 0;
-    if (status == MLFFPC_OK) {
+    int h_flag = h_flag_la;
+    if (status == MLFFPC_OK && !la) {
         cudaError_t e = cudaMemcpyAsync(ctx->h_scal, flag, sizeof(int), cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) status = cuda_fail(e, "pchol flag readback", __FILE__, __LINE__);

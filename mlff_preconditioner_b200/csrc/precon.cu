@@ -130,14 +130,18 @@ int mlffpc_woodbury_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, d
     MLFFPC_REQUIRE(Lt && W && k > 0 && ld >= ctx->n_local(), "woodbury_factor: bad argument");
     ProfWindow pw = prof_window("woodbury");
     pw.step(pw.first);
+    PhaseTimer pt((cudaStream_t)stream);
     int st = mlffpc_syrk_rows(ctx, Lt, k, ctx->n_local(), ld, lam, W, k, stream);
+    pt.lap("woodbury: gram");
     int info = 0;
     if (st == MLFFPC_OK) st = mlffpc_potrf_lower(ctx, W, k, k, &info, stream);
+    pt.lap("woodbury: potrf");
     if (st == MLFFPC_OK && info != 0) {
         set_error("%d-th leading minor of the array is not positive definite", info);
         st = MLFFPC_ERR_LINALG;
     }
     if (st == MLFFPC_OK) st = mlffpc_trsm_rows(ctx, W, k, k, Lt, ctx->n_local(), ld, stream);
+    pt.lap("woodbury: trsm");
     pw.end();
     return st;
 }
@@ -161,13 +165,14 @@ int mlffpc_orthonormal_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld
     };
     ProfWindow pw = prof_window("woodbury");
     pw.step(pw.first);
+    PhaseTimer pt(s);
     // CholeskyQR2 of L (rows of Lt):  Lt = C1 C2 Qt with Qt Qt^T = I to working precision (cond(L) << 1e8)
-    MLFFPC_TRY(mlffpc_syrk_rows(ctx, Lt, k, nl, ld, 0.0, W1, k, stream));
-    MLFFPC_TRY(chol(W1));
-    MLFFPC_TRY(mlffpc_trsm_rows(ctx, W1, k, k, Lt, nl, ld, stream));
-    MLFFPC_TRY(mlffpc_syrk_rows(ctx, Lt, k, nl, ld, 0.0, W2, k, stream));
-    MLFFPC_TRY(chol(W2));
-    MLFFPC_TRY(mlffpc_trsm_rows(ctx, W2, k, k, Lt, nl, ld, stream));
+    MLFFPC_TRY(mlffpc_syrk_rows(ctx, Lt, k, nl, ld, 0.0, W1, k, stream)); pt.lap("orthonormal: gram 1");
+    MLFFPC_TRY(chol(W1)); pt.lap("orthonormal: potrf 1");
+    MLFFPC_TRY(mlffpc_trsm_rows(ctx, W1, k, k, Lt, nl, ld, stream)); pt.lap("orthonormal: trsm 1");
+    MLFFPC_TRY(mlffpc_syrk_rows(ctx, Lt, k, nl, ld, 0.0, W2, k, stream)); pt.lap("orthonormal: gram 2");
+    MLFFPC_TRY(chol(W2)); pt.lap("orthonormal: potrf 2");
+    MLFFPC_TRY(mlffpc_trsm_rows(ctx, W2, k, k, Lt, nl, ld, stream)); pt.lap("orthonormal: trsm 2");
     // B = C1 C2 (lower triangular): L L^T = Q (B^T B) Q^T.   S = B^T B + lam I
     MLFFPC_TRY(dgemm(false, k, k, k, 1.0, W1, k, W2, k, 0.0, Mk, k, false, s));
     transpose_kernel<<<gt, bt, 0, s>>>(Mk, W2, k);                                   // W2 = B^T
@@ -185,6 +190,7 @@ int mlffpc_orthonormal_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld
     MLFFPC_TRY(dgemm(true, k, k, k, 1.0, W1, k, W1, k, 0.0, Mk, k, true, s));         // Mk = Y^T Y (lower tiles)
     mirror_shift_kernel<<<g2, 256, 0, s>>>(Mk, k, 0.0);
     MLFFPC_LAUNCH_CHECK();
+    pt.lap("orthonormal: k x k inverse Mk");
     pw.end();
     return MLFFPC_OK;
 }
@@ -195,7 +201,9 @@ int mlffpc_projected_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld, 
     MLFFPC_TRY(mlffpc_orthonormal_factor(ctx, Lt, k, ld, lam, Mk, W1, W2, stream));
     ProfWindow pw = prof_window("woodbury");
     pw.step(pw.first);
+    PhaseTimer pt((cudaStream_t)stream);
     const int st = gram_dd(ctx, Lt, k, ctx->n_local(), ld, E, k, 0.0, true, (cudaStream_t)stream, ctx->defect_mode == 2);
+    pt.lap("projected: defect E");
     pw.end();
     return st;
 }

@@ -100,7 +100,7 @@ class GDMLTrain(object):
             'solver_name': solver,
             'solver_tol': task['solver_tol'],
             'norm_y_train': norm_y_train,
-            'n_inducing_pts_init': task['n_inducing_pts_init'],
+            'n_inducing_pts_init': task.get('n_inducing_pts_init', 25),
             'z': task['z'],
             'idxs_train': task['idxs_train'],
             'md5_train': task.get('md5_train', 'n/a'),
@@ -111,7 +111,7 @@ class GDMLTrain(object):
             'f_err': {'mae': np.nan, 'rmse': np.nan},
             'R_desc': R_desc_host.T,
             'R_d_desc_alpha': r_d_desc_alpha,
-            'interact_cut_off': task['interact_cut_off'],
+            'interact_cut_off': task.get('interact_cut_off', None),
             'c': 0.0,
             'std': std,
             'sig': task['sig'],
@@ -120,7 +120,7 @@ class GDMLTrain(object):
             'perms': task['perms'],
             'tril_perms_lin': tril_perms_lin,
             'use_E': task['use_E'],
-            'use_cprsn': task['use_cprsn'],
+            'use_cprsn': task.get('use_cprsn', False),
         }
         if solver_resid is not None:
             model['solver_resid'] = solver_resid

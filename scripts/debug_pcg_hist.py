@@ -3,9 +3,11 @@
 (a) mlffpc_pcg, (b) the same recurrence as a torch host loop over the device GEMV, (c) the numpy oracle.
 Question: is 27/28 (device) vs 30 (numpy) iterations a property of the system (summation-order sensitive) or a bug?"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch
-from tests.conftest import load_golden
+from conftest import load_golden
 from mlff_preconditioner_b200.engine import Engine
 from oracle import sgdml_oracle as orc
 

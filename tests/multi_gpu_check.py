@@ -71,6 +71,26 @@ def main():
         print('  Woodbury apply sharded vs single: rel diff %.2e' % err, flush=True)
     assert err < (1e-3 if big else 1e-8), err      # the 1/lam = 1e10 amplification grows with ||L L^T||
 
+    # projected form: the cross-rank (hi, lo) fold of the Gram kernels gives every rank the same k x k matrices, and
+    # the sharded apply (one k-vector allreduce) equals the single-GPU one
+    Lt2, _, _, _ = eng.pchol_build(k)
+    Lt2_ref, _, _, _ = ref.pchol_build(k)
+    Qt, Mk, E = eng.projected_factor_(Lt2, lam)
+    Qt_ref, Mk_ref, E_ref = ref.projected_factor_(Lt2_ref, lam)
+    gath = [torch.empty_like(E) for _ in range(world)]
+    dist.all_gather(gath, E)
+    assert all(torch.equal(g_, gath[0]) for g_ in gath), 'defect matrix differs between ranks'
+    errE = float((E - E_ref).abs().max())
+    errQ = float((Qt - Qt_ref[:, sl]).abs().max())
+    z = eng.precon_apply(Qt, lam, 1.0, a[sl].contiguous(), Mk=Mk, E=E)
+    z_ref = ref.precon_apply(Qt_ref, lam, 1.0, a, Mk=Mk_ref, E=E_ref)
+    err = float((z - z_ref[sl]).norm() / z_ref[sl].norm())
+    if rank == 0:
+        print('  projected form sharded vs single: max |dE| %.2e (|E| max %.2e), max |dQ| %.2e, apply rel diff %.2e'
+              % (errE, float(E_ref.abs().max()), errQ, err), flush=True)
+    assert errE < 1e-16 and err < (1e-3 if big else 1e-8), (errE, err)
+    del Lt2, Lt2_ref, Qt, Mk, E, Qt_ref, Mk_ref, E_ref
+
     # matvecs
     v = torch.randn(n, dtype=torch.float64, device='cuda', generator=torch.Generator(device='cuda').manual_seed(2))
     mv = eng.matvec_free(v)
@@ -94,18 +114,23 @@ def main():
         del K_loc
 
     # full solves through the public entry point, sharded vs single GPU
-    combos = (('assembled', 'cholesky'), ('assembled_sym', 'cholesky'), ('matrix_free', 'cholesky'),
-              ('assembled', 'random_scores'))
+    combos = (('assembled', 'cholesky', 'woodbury'), ('assembled_sym', 'cholesky', 'woodbury'),
+              ('matrix_free', 'cholesky', 'woodbury'), ('assembled_sym', 'cholesky', 'projected'),
+              ('matrix_free', 'cholesky', 'projected'), ('assembled', 'random_scores', 'woodbury'),
+              ('matrix_free', 'lev_random', 'woodbury'))
     if big:
-        combos = (('matrix_free', 'cholesky'), ('assembled_sym', 'cholesky'))
+        combos = (('matrix_free', 'cholesky', 'projected'), ('assembled_sym', 'cholesky', 'projected'))
         torch.cuda.empty_cache()
     tol_solve = 1e-3 if big else 1e-5
-    for mode, variant in combos:
+    for mode, variant, form in combos:
         out = {}
         for tag, distributed in (('sharded', True), ('single', False)):
             task = dict(inp['task'])
-            task.update(kernel_mode=mode, distributed=distributed, solver_tol=tol_solve, _want_hist=True)
-            np.random.seed(0)
+            task.update(kernel_mode=mode, distributed=distributed, solver_tol=tol_solve, _want_hist=True,
+                        precon_form=form)
+            # the sharded run does NOT seed the ranks alike: rank 0's column draws are broadcast;
+            # the single-GPU comparison run uses rank 0's seed on every rank
+            np.random.seed(rank if distributed else 0)
             it = Iterative(None, None)
             alphas, iters, resid, rmse, idxs, conv, info = it.solve(
                 task, inp['R_desc'], inp['R_d_desc'], inp['tpl'], inp['y'], inp['y_std'],
@@ -117,14 +142,14 @@ def main():
             rs = y - ref.matvec_free(xs, alpha=-1.0, shift=lam)
             if rank == 0:
                 hist = it.timings.get('resid_hist_rel')
-                print('  %s/%s %s: iters %d, ||b - A x|| / ||b|| re-checked on one GPU = %.3e, history every 100: %s'
-                      % (mode, variant, tag, iters, float(rs.norm() / y.norm()),
+                print('  %s/%s/%s %s: iters %d, ||b - A x|| / ||b|| re-checked on one GPU = %.3e, history every 100: %s'
+                      % (mode, variant, form, tag, iters, float(rs.norm() / y.norm()),
                          ' '.join('%.2e' % v for v in (hist[::100] if hist is not None else []))), flush=True)
             it.engine.close()
         d = np.linalg.norm(out['sharded'][0] - out['single'][0]) / np.linalg.norm(out['single'][0])
         i1, i0 = out['sharded'][1], out['single'][1]
         if rank == 0:
-            print('  %s/%s: iters sharded %d single %d, |dalpha|/|alpha| = %.2e' % (mode, variant, i1, i0, d), flush=True)
+            print('  %s/%s/%s: iters sharded %d single %d, |dalpha|/|alpha| = %.2e' % (mode, variant, form, i1, i0, d), flush=True)
         assert d < (1e-2 if big else 1e-4), (mode, variant, d)   # both are tol-accurate solutions (tol 1e-3 when big)
         assert abs(i1 - i0) <= max(1, int(0.05 * i0)), (mode, variant, i1, i0)
         assert np.array_equal(out['sharded'][2], out['single'][2])

@@ -50,7 +50,7 @@ def test_descriptors_on_device(torch_cuda, golden, case):
     assert relerr(xd.cpu().numpy(), g['R_desc_T'].T) < 1e-15        # the reference's own descriptors
     xh, gh = Desc(N).from_R(g['R_train'].reshape(M, -1))
     assert np.abs(xd.cpu().numpy() - xh).max() <= 4e-16 * np.abs(xh).max()
-    assert np.abs(gd.cpu().numpy() - gh).max() <= 4e-16 * np.abs(gh).max()
+    assert np.abs(gd.cpu().numpy() - gh).max() <= 1e-14 * np.abs(gh).max()   # r^3 by two products vs numpy's power
 
 
 @pytest.mark.parametrize('case', CASES)
