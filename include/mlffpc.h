@@ -121,6 +121,8 @@ int mlffpc_symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full
  *   "gram_mode"       [1]  Gram matrices (mlffpc_syrk_rows) with (hi, lo) accumulation of the k-tile products;
  *                          0 = one running fp64 sum per entry (the round-1 kernel: 188 instead of the reference's 119
  *                          CG iterations on BASELINE.json configs[0])
+ *   "tma_rows"        [1]  "T r" of the preconditioner apply on the TMA-fed row-strip kernel (csrc/symtma.cu); 0 = the
+ *                          register-staged 4-row GEMV of round 1
  *   "defect_mode"     [1]  E = Q Q^T - I of the projected form from the DMMA kernel (1) or with exact products and sums
  *                          on the FP64 vector pipe (2, ~7x slower; the reference for the tests)
  *   "precon_reorth"   [0]  project the complement twice in the orthonormal-form preconditioner apply (Mk given, no E):

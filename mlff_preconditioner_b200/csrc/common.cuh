@@ -116,6 +116,10 @@ struct mlffpc_ctx {
     int precon_accuracy = 0;       // option "precon_accuracy": 1 = Kahan-compensated T r and T^T u (diagnostics)
     bool pchol_lookahead = true;   // option "pchol_lookahead": candidate-panel (blocked) pivoted Cholesky
     long long last_pchol_refills = 0;  // panel rebuilds of the last mlffpc_pchol_build (diagnostics)
+    bool tma_attr_symv = false, tma_attr_rows = false;  // cudaFuncSetAttribute done for this context's device
+    double* rows_ws = nullptr;     // scratch of the TMA row-strip GEMV (precon.cu), owned by the context
+    int64_t rows_ws_len = 0;
+    int tma_rows = 1;              // option "tma_rows": 1 = T r of the preconditioner apply on the TMA row-strip kernel
     bool use_symv = false;  // option "symmetric_gemv": the assembled operator is the symmetric tile storage (symop.cu)
     // small persistent device scratch owned by the ctx (scalars / partial reductions, a few KB)
     double* scal = nullptr;    // device scalars
@@ -174,6 +178,10 @@ int64_t symop_ws_bytes(const mlffpc_ctx* ctx);
 int symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full, double* y_local, double alpha,
                 double shift, void* workspace, double* partial_out, cudaStream_t s);
 int64_t symv_tma_ws_doubles(int64_t nr, int64_t nc);
+int64_t rows_tma_ws_doubles(int64_t nr, int64_t nc, int num_sms);
+bool rows_tma_usable(const double* A, int64_t ld, int64_t nr, int64_t nc);
+int rows_gemv_tma(mlffpc_ctx* ctx, const double* A, int64_t nr, int64_t nc, int64_t ld, const double* x, double* y,
+                  double alpha, double* wsd, cudaStream_t s);
 bool symv_tma_usable(const double* K, int64_t ld, int64_t nr);
 int symv_tile_tma(mlffpc_ctx* ctx, const double* K, int64_t ld, int64_t nr, int64_t nc, int diag, int packed,
                   const double* xr, const double* xc, double* wsd, double* out_c, double* out_r,

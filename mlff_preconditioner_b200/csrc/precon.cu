@@ -25,6 +25,23 @@ int ensure_reorth_scratch(mlffpc_ctx* ctx, int64_t k) {
     return MLFFPC_OK;
 }
 
+// w = T r on the local columns: the TMA row-strip kernel when the shapes allow it, else the register-staged GEMV
+static int factor_times_vec(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t nl, int64_t ld, const double* r, double* w,
+                            cudaStream_t s) {
+    if (ctx->tma_rows && rows_tma_usable(T, ld, k, nl)) {
+        const int64_t need = rows_tma_ws_doubles(k, nl, ctx->num_sms);
+        if (ctx->rows_ws_len < need) {
+            if (ctx->rows_ws) cudaFree(ctx->rows_ws);
+            ctx->rows_ws = nullptr;
+            ctx->rows_ws_len = 0;
+            MLFFPC_CUDA(cudaMalloc((void**)&ctx->rows_ws, (size_t)need * sizeof(double)));
+            ctx->rows_ws_len = need;
+        }
+        return rows_gemv_tma(ctx, T, k, nl, ld, r, w, 1.0, ctx->rows_ws, s);
+    }
+    return launch_gemv_rows(T, k, nl, ld, r, w, 1.0, 0.0, 0, s, false);
+}
+
 // u: device scratch of 4 k + 8 doubles.  Mk == NULL: Woodbury form z = sign (r - T^T T r) / lam.
 // Mk != NULL: T holds an orthonormal basis Q^T of range(L) and Mk = (Q^T L L^T Q + lam I)^{-1}:
 //   z = sign ( (r - Q (Q^T r)) / lam + Q Mk (Q^T r) ).
@@ -41,7 +58,7 @@ int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double
         double* w = u;
         double* g1 = u + ko;       // w - E w
         double* g2 = u + 2 * ko;   // Mk w
-        MLFFPC_TRY(launch_gemv_rows(T, k, nl, ld, r, w, 1.0, 0.0, 0, s, false));
+        MLFFPC_TRY(factor_times_vec(ctx, T, k, nl, ld, r, w, s));
         MLFFPC_TRY(comm_allreduce_sum(ctx->comm, w, (size_t)k, s));
         MLFFPC_TRY(launch_gemv_rows(E, k, k, k, w, g1, -1.0, 1.0, 0, s, false));
         MLFFPC_TRY(launch_gemv_rows(Mk, k, k, k, w, g2, 1.0, 0.0, 0, s, false));
@@ -57,8 +74,10 @@ int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double
         MLFFPC_TRY(launch_gemv_rows(T + h, k, nl - h, ld, r + h, u2, 1.0, 0.0, 0, s, false));
         add_inplace_kernel<<<(unsigned)((k + 255) / 256), 256, 0, s>>>(u, u2, k);
         MLFFPC_LAUNCH_CHECK();
-    } else {
+    } else if (comp) {
         MLFFPC_TRY(launch_gemv_rows(T, k, nl, ld, r, u, 1.0, 0.0, 0, s, comp));
+    } else {
+        MLFFPC_TRY(factor_times_vec(ctx, T, k, nl, ld, r, u, s));
     }
     MLFFPC_TRY(comm_allreduce_sum(ctx->comm, u, (size_t)k, s));
     if (Mk && ctx->precon_reorth && ctx->reorth_scratch) {

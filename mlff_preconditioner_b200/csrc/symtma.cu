@@ -209,6 +209,113 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symv_tma_kernel(const SymTmaArg
     }
 }
 
+// ---- one-sided variant: y = A x for a wide matrix with FEW rows (the k x n_local preconditioner factor) ---------
+// Same pipeline (persistent CTAs, TMA-fed 3-stage ring of 32 x 256 units, row sums in registers), no column sums.
+// The register-staged gemv_rows kernel needs rows / 4 CTAs' worth of loads in flight and reaches ~0.76 of the HBM
+// rate on 4839 rows; here the TMA keeps ~128 KB per SM in flight regardless of the row count.  A strip of 32 rows may
+// be shared by several CTAs (few rows, many SMs): CTA b writes its partial row sums into slot b - first_cta(strip);
+// a small kernel adds the slots in order (deterministic).
+struct RowsTmaArgs {
+    int64_t nr, nc, nstrips, ups, units_total, units_per_cta;
+    int nslots;
+    const CUtensorMap* tmap;
+    const double* x;
+    double* rowpart;  // [nstrips, nslots, 32]
+};
+
+__global__ void __launch_bounds__(ST_THREADS, 1) rows_tma_kernel(const RowsTmaArgs a) {
+    extern __shared__ unsigned char st_smem_raw[];
+    unsigned char* sm = (unsigned char*)(((uintptr_t)st_smem_raw + 1023) & ~(uintptr_t)1023);
+    double* tiles = (double*)sm;
+    unsigned char* small = sm + (size_t)ST_STAGES * ST_STAGE_BYTES;
+    uint64_t* full_bar = (uint64_t*)small;
+    uint64_t* empty_bar = full_bar + ST_STAGES;
+    double* red = (double*)(small + 64);  // [32][4]
+
+    const int tid = threadIdx.x;
+    const int64_t u0 = (int64_t)blockIdx.x * a.units_per_cta;
+    int64_t u1 = u0 + a.units_per_cta;
+    if (u1 > a.units_total) u1 = a.units_total;
+    if (u0 >= u1) return;
+    if (tid == 0) {
+        for (int i = 0; i < ST_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], ST_CONSUMERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int64_t s = u0 / a.ups, j = u0 % a.ups;
+
+    if (tid >= ST_CONSUMERS) {
+        if (tid == ST_CONSUMERS) {
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t u = u0; u < u1; ++u) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], ST_STAGE_BYTES);
+                tma_load_2d(tiles + (size_t)stage * (ST_ROWS * ST_COLS), a.tmap, &full_bar[stage], (int)(j * ST_COLS),
+                            (int)(s * ST_ROWS), policy);
+                if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+                if (++j == a.ups) { ++s; j = 0; }
+            }
+        }
+        return;
+    }
+
+    const int lane = tid & 31, warp = tid >> 5;
+    double acc[ST_ROWS];
+#pragma unroll
+    for (int i = 0; i < ST_ROWS; ++i) acc[i] = 0.0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t u = u0; u < u1; ++u) {
+        const int64_t col0 = j * ST_COLS;
+        const int w = (int)((a.nc - col0 < ST_COLS) ? (a.nc - col0) : ST_COLS);
+        double2 xv = make_double2(0.0, 0.0);   // columns past nc are zero-filled by the tensor map; x = 0 there as well
+        if (2 * tid < w) xv.x = __ldg(a.x + col0 + 2 * tid);
+        if (2 * tid + 1 < w) xv.y = __ldg(a.x + col0 + 2 * tid + 1);
+        mbar_wait(&full_bar[stage], phase);
+        const double2* tp = reinterpret_cast<const double2*>(tiles + (size_t)stage * (ST_ROWS * ST_COLS)) + tid;
+#pragma unroll
+        for (int i = 0; i < ST_ROWS; ++i) {
+            const double2 kv = tp[i * (ST_COLS / 2)];
+            acc[i] = fma(kv.y, xv.y, fma(kv.x, xv.x, acc[i]));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+        if (j + 1 == a.ups || u + 1 == u1) {
+#pragma unroll
+            for (int i = 0; i < ST_ROWS; ++i) {
+                const double v = warp_sum(acc[i]);
+                if (lane == 0) red[i * 4 + warp] = v;
+                acc[i] = 0.0;
+            }
+            consumer_bar();
+            if (tid < ST_ROWS) {
+                const int slot = (int)((int64_t)blockIdx.x - (s * a.ups) / a.units_per_cta);
+                a.rowpart[(s * a.nslots + slot) * ST_ROWS + tid] =
+                    (red[tid * 4 + 0] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]);
+            }
+            consumer_bar();
+        }
+        if (++j == a.ups) { ++s; j = 0; }
+    }
+}
+
+__global__ void rows_tma_reduce_kernel(const double* __restrict__ rowpart, int nslots, int64_t nr, double* __restrict__ y,
+                                       double alpha) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nr) return;
+    const int64_t s = r / ST_ROWS, i = r % ST_ROWS;
+    double t = 0.0;
+    for (int q = 0; q < nslots; ++q) t += rowpart[(s * nslots + q) * ST_ROWS + i];
+    y[r] = alpha * t;
+}
+
 // columns: out_c[c] = post( [diag: rowsum(c)] + sum_{s >= s_min(c)} ws[s, c] );  rows (off-diagonal): out_r[r] += rowsum(r)
 constexpr int STR_COLS = 64, STR_SPLIT = 4;
 __global__ void __launch_bounds__(STR_COLS * STR_SPLIT)
@@ -335,6 +442,82 @@ static int get_tmaps(const double* K, int64_t ld, int64_t nr, int packed, cudaSt
     return MLFFPC_OK;
 }
 
+struct RowsPlan {
+    int64_t nstrips, ups, units_total, units_per_cta, ncta;
+    int nslots;
+};
+static RowsPlan rows_plan(int64_t nr, int64_t nc, int num_sms) {
+    RowsPlan p;
+    p.nstrips = (nr + ST_ROWS - 1) / ST_ROWS;
+    p.ups = (nc + ST_COLS - 1) / ST_COLS;
+    p.units_total = p.nstrips * p.ups;
+    p.units_per_cta = (p.units_total + num_sms - 1) / num_sms;
+    if (p.units_per_cta < 4) p.units_per_cta = 4;  // a CTA should amortise its pipeline fill
+    p.ncta = (p.units_total + p.units_per_cta - 1) / p.units_per_cta;
+    p.nslots = (int)((p.ups + p.units_per_cta - 1) / p.units_per_cta) + 1;
+    return p;
+}
+int64_t rows_tma_ws_doubles(int64_t nr, int64_t nc, int num_sms) {
+    const RowsPlan p = rows_plan(nr, nc, num_sms);
+    return p.nstrips * p.nslots * ST_ROWS + 64;
+}
+bool rows_tma_usable(const double* A, int64_t ld, int64_t nr, int64_t nc) {
+    return ((uintptr_t)A % 16 == 0) && (ld % 2 == 0) && ld < ((int64_t)1 << 31) && nr < ((int64_t)1 << 31) && nc >= 1024 &&
+           get_encode_tiled() != nullptr;
+}
+// y[nr] = alpha * A x for row-major A[nr, nc] (pitch ld); wsd: rows_tma_ws_doubles(nr, nc, num_sms) doubles
+int rows_gemv_tma(mlffpc_ctx* ctx, const double* A, int64_t nr, int64_t nc, int64_t ld, const double* x, double* y,
+                  double alpha, double* wsd, cudaStream_t s) {
+    RowsTmaArgs a;
+    // the map spans exactly nc columns: the TMA zero-fills the ragged last unit (pitch ld in the global stride)
+    {
+        std::lock_guard<std::mutex> lk(g_tmap_mu);
+        int device = 0;
+        MLFFPC_CUDA(cudaGetDevice(&device));
+        const CUtensorMap* found = nullptr;
+        for (const auto& e : g_tmaps)
+            if (e.base == A && e.ld == ld && e.nr == nr && e.packed == (int)(2 + (nc & 0xffffff)) && e.device == device) found = e.dev;
+        if (!found) {
+            encode_tiled_fn enc = get_encode_tiled();
+            if (!enc) { set_error("rows_gemv_tma: cuTensorMapEncodeTiled is not available from this driver"); return MLFFPC_ERR_CUDA; }
+            CUtensorMap host;
+            const cuuint64_t gdim[2] = {(cuuint64_t)nc, (cuuint64_t)nr};
+            const cuuint64_t gstride[1] = {(cuuint64_t)ld * 8};
+            const cuuint32_t box[2] = {ST_COLS, ST_ROWS};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult r = enc(&host, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(A), gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("rows_gemv_tma: cuTensorMapEncodeTiled failed (%d)", (int)r); return MLFFPC_ERR_CUDA; }
+            TmapEntry e;
+            e.base = A; e.ld = ld; e.nr = nr; e.packed = (int)(2 + (nc & 0xffffff)); e.device = device;
+            MLFFPC_CUDA(cudaMalloc(&e.dev, sizeof(CUtensorMap)));
+            MLFFPC_CUDA(cudaMemcpy(e.dev, &host, sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+            if (g_tmaps.size() >= 32) {
+                cudaFree(g_tmaps.front().dev);
+                g_tmaps.erase(g_tmaps.begin());
+            }
+            g_tmaps.push_back(e);
+            found = e.dev;
+        }
+        a.tmap = found;
+    }
+    const RowsPlan p = rows_plan(nr, nc, ctx->num_sms);
+    a.nr = nr; a.nc = nc; a.nstrips = p.nstrips; a.ups = p.ups; a.units_total = p.units_total;
+    a.units_per_cta = p.units_per_cta; a.nslots = p.nslots;
+    a.x = x; a.rowpart = wsd;
+    MLFFPC_CUDA(cudaMemsetAsync(wsd, 0, (size_t)(p.nstrips * p.nslots * ST_ROWS) * 8, s));
+    if (!ctx->tma_attr_rows) {
+        MLFFPC_CUDA(cudaFuncSetAttribute(rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+        ctx->tma_attr_rows = true;
+    }
+    rows_tma_kernel<<<(unsigned)p.ncta, ST_THREADS, ST_SMEM, s>>>(a);
+    MLFFPC_LAUNCH_CHECK();
+    rows_tma_reduce_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(wsd, p.nslots, nr, y, alpha);
+    MLFFPC_LAUNCH_CHECK();
+    return MLFFPC_OK;
+}
+
 int64_t symv_tma_ws_doubles(int64_t nr, int64_t nc) {
     const int64_t nstrips = (nr + ST_ROWS - 1) / ST_ROWS;
     const int64_t ld_ws = ((nc + 1) & ~(int64_t)1) + ST_COLS;  // the last unit of a strip may store past nc
@@ -369,10 +552,9 @@ int symv_tile_tma(mlffpc_ctx* ctx, const double* K, int64_t ld, int64_t nr, int6
     a.ws = wsd;
     a.rowpart = wsd + a.nstrips * a.ld_ws;
     MLFFPC_CUDA(cudaMemsetAsync(a.rowpart, 0, (size_t)a.nstrips * 2 * ST_ROWS * 8, s));
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->tma_attr_symv) {  // per context (= per device): cudaFuncSetAttribute applies to the current device only
         MLFFPC_CUDA(cudaFuncSetAttribute(symv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
-        attr_set = true;
+        ctx->tma_attr_symv = true;
     }
     symv_tma_kernel<<<(unsigned)ncta, ST_THREADS, ST_SMEM, s>>>(a);
     MLFFPC_LAUNCH_CHECK();

@@ -114,6 +114,113 @@ def _sharded_pcg(A_rows, b_local, T_local, lam, row0, n, tol, maxiter):
     return x, it, info
 
 
+def _sharded_pchol_merged(A_rows, diag_local, row0, n, k):
+    """The round-2 step protocol of csrc/pchol.cu (host-free look-ahead stepping): ONE allgather per step carries every
+    rank's best candidate together with that candidate's factor row, every rank picks the winner from the gathered
+    messages, and the swap of step m is applied to index_columns / pos only at the start of step m + 1 -- the update
+    of step m derives the new positions locally from the untouched arrays."""
+    nl = A_rows.shape[0]
+    index_columns = np.arange(n)
+    pos = np.arange(n)
+    Lt = np.zeros((k, nl))
+    diag = diag_local.copy()
+    pending = None
+    for m in range(k):
+        if pending is not None:                      # prepare kernel: apply the previous step's swap
+            mp_, pi_ = pending
+            i_argmax, e = pos[pi_], index_columns[mp_]
+            index_columns[mp_], index_columns[i_argmax] = pi_, e
+            pos[pi_], pos[e] = mp_, i_argmax
+            pending = None
+        cand = np.array([-1e300, 1e300, -1.0])
+        for r in range(nl):
+            g = row0 + r
+            if pos[g] >= m and (diag[r] > cand[0] or (diag[r] == cand[0] and pos[g] < cand[1])):
+                cand = np.array([diag[r], float(pos[g]), float(g)])
+        msg = np.zeros(4 + k)
+        msg[:3] = cand
+        if cand[2] >= 0:
+            msg[4:4 + m] = Lt[:m, int(cand[2]) - row0]
+        best, lrow = None, None
+        for c in _allgather(msg):                     # update kernel: winner among the ranks' messages
+            if best is None or c[0] > best[0] or (c[0] == best[0] and c[1] < best[1]):
+                best, lrow = c[:3], c[4:4 + m]
+        pi = int(best[2])
+        lpiv = np.sqrt(best[0])
+        e, i_argmax = index_columns[m], pos[pi]       # arrays still hold the state before this step's swap
+        col = A_rows[:, pi]
+        for r in range(nl):
+            g = row0 + r
+            ps = i_argmax if (g == e and g != pi) else pos[g]
+            if g == pi:
+                Lt[m, r] = lpiv
+            elif ps > m:
+                l = (col[r] - Lt[:m, r] @ lrow) / lpiv
+                Lt[m, r] = l
+                diag[r] -= l * l
+        pending = (m, pi)
+    if pending is not None:                           # flush kernel
+        mp_, pi_ = pending
+        i_argmax, e = pos[pi_], index_columns[mp_]
+        index_columns[mp_], index_columns[i_argmax] = pi_, e
+        pos[pi_], pos[e] = mp_, i_argmax
+    return Lt, index_columns
+
+
+def _sharded_pcg_deferred(A_rows, b_local, T_local, lam, row0, n, tol, maxiter):
+    """The round-2 loop of csrc/pcg.cu: ||r||^2 of iteration j travels with rho of iteration j + 1 in ONE two-element
+    allreduce; the stopping test of iteration j runs at the start of the p-update of iteration j + 1 and freezes x, r, p
+    (every later kernel is a no-op); on a hit after iteration 1 the true residual is recomputed once (legacy scipy)."""
+    nl = A_rows.shape[0]
+
+    def precon(r):
+        u = _allreduce(T_local @ r)
+        return (r - T_local.T @ u) / lam
+
+    def gather(v_local):
+        return np.concatenate(_allgather(v_local))
+
+    x = np.zeros(nl)
+    bnrm2 = np.sqrt(_allreduce(np.array([b_local @ b_local]))[0])
+    r = b_local - A_rows @ gather(x)
+    atol2 = (tol * bnrm2) ** 2
+    red = np.zeros(4)                      # rho, rr(prev), p.q, rho_prev -- local until allreduced
+    red[1] = r @ r
+    p = np.zeros(nl)
+    frozen, conv_iter, it = False, None, 0
+    while it < maxiter + 1:                # one extra pass: the test of the last iteration
+        it += 1
+        z = precon(r)
+        if not frozen:
+            red[0] = r @ z
+        red[:2] = _allreduce(red[:2])
+        if it > 1 and not frozen and red[1] <= atol2:
+            frozen, conv_iter = True, it - 1
+        if frozen:
+            # host side: recompute the true residual once (it > 1), accept or unfreeze
+            if conv_iter > 1:
+                r = b_local - A_rows @ gather(x)
+                rr = _allreduce(np.array([r @ r]))[0]
+            else:
+                rr = red[1]
+            if rr <= atol2:
+                return x, conv_iter, 0
+            frozen, it = False, conv_iter
+            red[1] = r @ r
+            continue
+        if it > maxiter:
+            break
+        p = z.copy() if it == 1 else z + (red[0] / red[3]) * p
+        q = A_rows @ gather(p)
+        red[2] = _allreduce(np.array([p @ q]))[0]
+        alpha = red[0] / red[2]
+        x += alpha * p
+        r -= alpha * q
+        red[1] = r @ r                     # local; allreduced together with the next rho
+        red[3] = red[0]
+    return x, maxiter, 1
+
+
 def _worker(rank, world, port, q):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -141,7 +248,15 @@ def _worker(rank, world, port, q):
         # Woodbury factor from the reduced Gram, then the sharded PCG
         W = _allreduce(Lt @ Lt.T) + lam * np.eye(k)
         T_local = np.linalg.solve(np.linalg.cholesky(W), Lt)
+        # round-2 protocols: merged candidate + row message with deferred swaps; deferred stopping test
+        Lt2, idx2 = _sharded_pchol_merged(A[row0:row1], g['diag'][row0:row1], row0, n, k)
+        assert np.array_equal(idx2, idx) and np.array_equal(Lt2, Lt)
+        x2, iters2, info2 = _sharded_pcg_deferred(A[row0:row1], g['y'][row0:row1], T_local, lam, row0, n, 1e-4, 5 * n)
         x, iters, info = _sharded_pcg(A[row0:row1], g['y'][row0:row1], T_local, lam, row0, n, 1e-4, 5 * n)
+        assert (iters2, info2) == (iters, info) and np.array_equal(x2, x)
+        x3, iters3, info3 = _sharded_pcg_deferred(A[row0:row1], g['y'][row0:row1], T_local, lam, row0, n, 1e-30, 7)
+        x4, iters4, info4 = _sharded_pcg(A[row0:row1], g['y'][row0:row1], T_local, lam, row0, n, 1e-30, 7)
+        assert (iters3, info3) == (7, 1) and iters4 == 7 and info4 == 1 and np.array_equal(x3, x4)
         L_full = g['L']
         T_ref = orc.woodbury_factor(L_full, lam)
         x_ref, it_ref, _, info_ref = orc.pcg(lambda v: A @ v, g['y'], lambda a: orc.woodbury_apply(T_ref, lam, a),
@@ -162,7 +277,7 @@ def test_partition_covers_rows():
     from mlff_preconditioner_b200.dist import shard_slices
     from mlff_preconditioner_b200.engine import shard_points
 
-    for M, world in [(12, 2), (4000, 8), (10000, 8), (7, 3), (9, 4)]:
+    for M, world in [(12, 2), (4000, 8), (10000, 8), (7, 3), (20000, 8)]:
         sl = shard_slices(M, 27, world)
         assert sl[0][0] == 0 and max(s[1] for s in sl) == M * 27
         for (a0, a1), (b0, b1) in zip(sl[:-1], sl[1:]):
@@ -173,6 +288,11 @@ def test_partition_covers_rows():
                 assert shard_points(M, r, world) == (r * ppr, min((r + 1) * ppr, M))
     with pytest.raises(ValueError):
         shard_points(2, 3, 4)
+    # a world size that would leave the last rank without points is refused on EVERY rank (a rank-local error would
+    # leave the others blocked in their first collective): M = 9 on 4 ranks -> 3 points per rank, rank 3 empty
+    for r in range(4):
+        with pytest.raises(ValueError):
+            shard_points(9, r, 4)
 
 
 @pytest.mark.timeout(300)

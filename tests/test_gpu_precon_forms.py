@@ -249,3 +249,30 @@ def test_default_form_is_the_reference_formula(torch_cuda):
         task['precon_form'] = 'nonsense'
         Iterative(None, None).solve(task, d['R_desc'], d['R_d_desc'], d['tpl'], d['y'], 1.0, break_percentage=0.1,
                                     str_preconditioner='cholesky')
+
+
+@pytest.mark.parametrize('k', [5, 33, 540, 1000])
+def test_tma_row_strip_gemv_equals_register_gemv(torch_cuda, k):
+    """'T r' of the apply on the TMA row-strip kernel (option tma_rows = 1, default) against the register-staged GEMV
+    (tma_rows = 0) and numpy: few rows (several CTAs per 32-row strip), rows not a multiple of 32, columns not a
+    multiple of 256 (n_local = 5400), and a padded leading dimension."""
+    torch = torch_cuda
+    eng, d = _seeded_engine(M=200)
+    lam = 1e-10
+    rng = np.random.default_rng(k)
+    Tn = rng.standard_normal((k, eng.n_local)) / np.sqrt(eng.n_local)
+    a_np = rng.standard_normal(eng.n_local)
+    a = torch.as_tensor(a_np, device=eng.device)
+    ref = (a_np - Tn.T @ (Tn @ a_np)) / lam
+    for ld in (eng.n_local, eng.n_local + 6):
+        buf = torch.zeros((k, ld), dtype=torch.float64, device=eng.device)
+        buf[:, :eng.n_local] = torch.as_tensor(Tn, device=eng.device)
+        T = buf[:, :eng.n_local]
+        eng.set_option('tma_rows', 1)
+        z1 = eng.precon_apply(T, lam, 1.0, a).cpu().numpy()
+        z1b = eng.precon_apply(T, lam, 1.0, a).cpu().numpy()
+        eng.set_option('tma_rows', 0)
+        z0 = eng.precon_apply(T, lam, 1.0, a).cpu().numpy()
+        eng.set_option('tma_rows', 1)
+        assert np.array_equal(z1, z1b)                     # deterministic
+        assert relerr(z1, ref) < 1e-11 and relerr(z0, ref) < 1e-11 and relerr(z1, z0) < 1e-12
