@@ -521,6 +521,9 @@ def run_ours(args):
                 roofline['traffic_source'] = tr['source']
         except Exception:
             pass
+    line_collectives = ('none (one GPU)' if world == 1 else
+                        ('NVLink peer memory, fused into the solver kernels (CUDA IPC; NCCL only for set-up, the Gram '
+                         'reduction and the panel rebuilds)' if tm.get('peer_collectives') else 'NCCL'))
     phases = {'preconditioner_s': tm['preconditioner'], 'pchol_build_s': tm.get('pchol_build'),
               'assemble_s': tm['assemble'], 'cg_s': tm['cg'], 'cg_iters': iters, 'resid': resid,
               'rel_resid': resid / np.linalg.norm(inp['y']), 'converged': info == 0,
@@ -579,7 +582,7 @@ def run_ours(args):
         'metric': 'pcg_time_to_solution', 'value': value, 'unit': 's', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': value * 1e3, 'higher_is_better': False, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(inp, args, world),
-        'clocks': clocks,
+        'clocks': clocks, 'collectives': line_collectives,
         'e2e': {'value': e2e_s, 'unit': 's', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'steps': e2e_steps, 'api': 'Iterative.solve(task, R_desc, R_d_desc, tril_perms_lin, y, y_std, ...)',
                 'alphas_rel_diff_vs_device_arm': agree},

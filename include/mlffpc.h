@@ -48,6 +48,19 @@ int mlffpc_comm_init(mlffpc_ctx* ctx, const char* libnccl_path, const void* id12
 int mlffpc_allreduce_sum(mlffpc_ctx* ctx, double* buf, int64_t count, void* stream);
 int mlffpc_allgather(mlffpc_ctx* ctx, const void* send, void* recv, int64_t bytes_per_rank, void* stream);
 
+/* NVLink peer-memory collectives (optional, after comm_init and set_geometry; csrc/peer.cuh).  Every rank allocates one
+ * communication buffer and exports a 64-byte CUDA IPC handle; the host gathers the handles (torch.distributed) and
+ * every rank maps all of them.  From then on the small collectives of the inner loops are fused into the solver's own
+ * kernels: the dot-product kernels push their scalars into the peers' slots and the update kernels combine them, the
+ * p-update kernel stores the search direction into every rank's replicated vector, the symmetric operator's finish
+ * kernel pulls the peers' partial products (fused reduce-scatter), the pivot step's prepare kernel pushes
+ * {candidate, factor row} -- no library collective per CG iteration / pivot step.  k_max bounds the k-vector of the
+ * preconditioner apply that can travel this way (larger k falls back to ncclAllReduce).  When export or import fails on
+ * ANY rank, call mlffpc_peer_disable on ALL ranks: the NCCL path is the fallback. */
+int mlffpc_peer_export(mlffpc_ctx* ctx, int64_t k_max, void* handle64_out);
+int mlffpc_peer_import(mlffpc_ctx* ctx, const void* handles /* world * 64 bytes, rank order */, int count);
+int mlffpc_peer_disable(mlffpc_ctx* ctx);
+
 /* ---------------------------------------------------------------- geometry ---- */
 /* Replaces the per-call re-upload of descriptors in GDMLTorchPredict.__init__ (torchtools.py:80-97)
  * and the (R_desc, R_d_desc, tril_perms_lin) arguments every reference routine takes.
@@ -121,6 +134,7 @@ int mlffpc_symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full
  *   "gram_mode"       [1]  Gram matrices (mlffpc_syrk_rows) with (hi, lo) accumulation of the k-tile products;
  *                          0 = one running fp64 sum per entry (the round-1 kernel: 188 instead of the reference's 119
  *                          CG iterations on BASELINE.json configs[0])
+ *   "peer_kvec", "peer_pivots" [1]  use the mapped peer buffers for the apply's k-vector sum / the pivot-step message
  *   "tma_rows"        [1]  "T r" of the preconditioner apply on the TMA-fed row-strip kernel (csrc/symtma.cu); 0 = the
  *                          register-staged 4-row GEMV of round 1
  *   "defect_mode"     [1]  E = Q Q^T - I of the projected form from the DMMA kernel (1) or with exact products and sums

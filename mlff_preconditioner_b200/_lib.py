@@ -27,6 +27,9 @@ SIGNATURES = {
     'mlffpc_destroy': [c_ptr],
     'mlffpc_comm_unique_id': [c_str, c_ptr],
     'mlffpc_comm_init': [c_ptr, c_str, c_ptr, c_int, c_int],
+    'mlffpc_peer_export': [c_ptr, c_i64, c_ptr],
+    'mlffpc_peer_import': [c_ptr, c_ptr, c_int],
+    'mlffpc_peer_disable': [c_ptr],
     'mlffpc_allreduce_sum': [c_ptr, c_ptr, c_i64, c_ptr],
     'mlffpc_allgather': [c_ptr, c_ptr, c_ptr, c_i64, c_ptr],
     'mlffpc_geometry_workspace_bytes': [c_i64, c_int, c_int, ctypes.POINTER(c_i64)],

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmlffpc.so')
-SOURCES = ['core.cu', 'geometry.cu', 'matvec.cu', 'gemv.cu', 'symop.cu', 'symtma.cu', 'dense.cu', 'gramdd.cu', 'pchol.cu', 'precon.cu', 'pcg.cu']
+SOURCES = ['core.cu', 'geometry.cu', 'matvec.cu', 'gemv.cu', 'symop.cu', 'symtma.cu', 'dense.cu', 'gramdd.cu', 'pchol.cu', 'precon.cu', 'pcg.cu', 'peer.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=default', '--use_fast_math=false']
 

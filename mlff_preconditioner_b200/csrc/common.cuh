@@ -74,6 +74,8 @@ int comm_allgather(Comm& c, const void* send, void* recv, size_t bytes_per_rank,
 int comm_broadcast(Comm& c, void* buf, size_t bytes, int root, cudaStream_t s);
 int comm_reduce_scatter_sum(Comm& c, const double* send, double* recv, size_t count_per_rank, cudaStream_t s);
 
+struct Peer;  // NVLink peer-memory collectives (peer.cuh)
+
 }  // namespace mlffpc
 
 // The opaque context.  Holds no large allocations: geometry tables live in caller-owned workspace.
@@ -98,6 +100,7 @@ struct mlffpc_ctx {
     int64_t n_local() const { return (pt1 - pt0) * (int64_t)dim_i; }
     int64_t row0() const { return pt0 * (int64_t)dim_i; }
     mlffpc::Comm comm;
+    mlffpc::Peer* peer = nullptr;  // mapped peer buffers (mlffpc_peer_export / _import); NULL: NCCL only
     // partition used by the symmetric tile operator; follows the communicator unless overridden by the
     // options "layout_rank"/"layout_world" (rank emulation on one GPU, tests only)
     int lay_rank = 0, lay_world = 1;
@@ -119,6 +122,8 @@ struct mlffpc_ctx {
     bool tma_attr_symv = false, tma_attr_rows = false;  // cudaFuncSetAttribute done for this context's device
     double* rows_ws = nullptr;     // scratch of the TMA row-strip GEMV (precon.cu), owned by the context
     int64_t rows_ws_len = 0;
+    bool peer_pivots = true;       // option "peer_pivots": pivot-step message over peer memory when mapped
+    bool peer_kvec = true;         // option "peer_kvec": k-vector allreduce of the apply over peer memory when mapped
     int tma_rows = 1;              // option "tma_rows": 1 = T r of the preconditioner apply on the TMA row-strip kernel
     bool use_symv = false;  // option "symmetric_gemv": the assembled operator is the symmetric tile storage (symop.cu)
     // small persistent device scratch owned by the ctx (scalars / partial reductions, a few KB)
@@ -204,6 +209,15 @@ int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double
                  const double* E = nullptr);
 
 int ensure_reorth_scratch(mlffpc_ctx* ctx, int64_t k);
+// peer-memory collectives (peer.cu)
+bool peer_on(const mlffpc_ctx* ctx);
+int peer_allreduce_kvec(mlffpc_ctx* ctx, double* w, int64_t k, cudaStream_t s);
+int peer_wait(mlffpc_ctx* ctx, int ch, uint64_t epoch, const int* frozen, cudaStream_t s);
+void peer_destroy(mlffpc_ctx* ctx);
+int64_t peer_kmax(const mlffpc_ctx* ctx);
+double* peer_yp_local(const mlffpc_ctx* ctx);
+int symop_finish_peer(mlffpc_ctx* ctx, const double* x_local, double* y_local, int64_t nl, int64_t g_off, double alpha,
+                      double shift, cudaStream_t s);
 // W = X X^T + shift I (or X X^T - I) with extended-precision accumulation, summed over ranks (gramdd.cu)
 int gram_dd(mlffpc_ctx* ctx, const double* X, int64_t m, int64_t n_cols, int64_t ldx, double* out, int64_t ld_out,
             double shift, bool minus_identity, cudaStream_t s, bool exact = false);

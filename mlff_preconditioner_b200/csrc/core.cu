@@ -203,6 +203,7 @@ int mlffpc_destroy(mlffpc_ctx* ctx) {
     if (ctx->partials) cudaFree(ctx->partials);
     if (ctx->reorth_scratch) cudaFree(ctx->reorth_scratch);
     if (ctx->rows_ws) cudaFree(ctx->rows_ws);
+    peer_destroy(ctx);
     delete ctx;
     return MLFFPC_OK;
 }
@@ -249,6 +250,8 @@ int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value) {
         return MLFFPC_OK;
     }
     if (nm == "assemble_legacy") { ctx->assemble_legacy = value != 0; return MLFFPC_OK; }
+    if (nm == "peer_pivots") { ctx->peer_pivots = value != 0; return MLFFPC_OK; }
+    if (nm == "peer_kvec") { ctx->peer_kvec = value != 0; return MLFFPC_OK; }
     if (nm == "tma_rows") { ctx->tma_rows = value != 0 ? 1 : 0; return MLFFPC_OK; }
     if (nm == "defect_mode") { ctx->defect_mode = value == 2 ? 2 : 1; return MLFFPC_OK; }
     if (nm == "gram_mode") { ctx->gram_mode = value != 0 ? 1 : 0; return MLFFPC_OK; }

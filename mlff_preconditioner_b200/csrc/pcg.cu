@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace mlffpc {
 
@@ -37,7 +38,36 @@ struct PcgState {
     double last_rr;    // ||r||^2 of last_iter (global)
     double pad;
 };
-// red[0] = rho (r.z), red[1] = ||r||^2 of the previous update, red[2] = p.q, red[3] = rho of the previous iteration
+// red[0] = rho (r.z), red[1] = ||r||^2 of the previous update, red[2] = p.q, red[3] = rho of the previous iteration,
+// red[6] = rho of this iteration summed over ranks (written by the p-update, read by the x,r-update)
+
+// One fused scalar exchange over peer memory (peer.cuh): the producing kernel pushes into slot `parity` of channel `ch`,
+// the consuming kernel waits for epoch and adds the ranks' slots in rank order.  on = 0: NCCL has already summed red[].
+struct PeerXchg {
+    PeerView pv;
+    int on, ch, parity;
+    uint64_t epoch;
+};
+__device__ __forceinline__ void peer_push_scalars(const PeerXchg& x, double v0, double v1) {
+    for (int r = 0; r < x.pv.world; ++r) {
+        double* dst = x.pv.scal(r, x.parity, x.pv.rank);
+        dst[0] = v0;
+        dst[1] = v1;
+    }
+    peer_signal_all(x.pv, x.ch, x.epoch);
+}
+// one thread: wait for every rank's push, return the rank-ordered sums
+__device__ __forceinline__ void peer_sum_scalars(const PeerXchg& x, double& v0, double& v1) {
+    peer_wait_all(x.pv, x.ch, x.epoch);
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < x.pv.world; ++r) {
+        const double* src = x.pv.scal(x.pv.rank, x.parity, r);
+        a += peer_ld(src);
+        b += peer_ld(src + 1);
+    }
+    v0 = a;
+    v1 = b;
+}
 
 // deterministic grid reduction: per-block partials, the last block to finish sums them in index order
 __device__ __forceinline__ bool grid_reduce(double v, double* partials, unsigned* counter, double* result) {
@@ -63,24 +93,41 @@ __device__ __forceinline__ bool grid_reduce(double v, double* partials, unsigned
     return threadIdx.x == 0;
 }
 
-// out = sum a[i] b[i]  (state == NULL: unconditional; otherwise the store is skipped while frozen)
+// out = sum a[i] b[i]  (state == NULL: unconditional; otherwise the store is skipped while frozen).  With a peer
+// exchange the last block also pushes (result, *extra) to every rank -- the collective is part of this kernel.
 __global__ void dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
-                           double* partials, unsigned* counter, double* out, const PcgState* state) {
+                           double* partials, unsigned* counter, double* out, const PcgState* state,
+                           const PeerXchg px, const double* extra) {
     if (state && state->frozen) return;
     double v = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         v = fma(a[i], b[i], v);
     __shared__ double res;
-    if (grid_reduce(v, partials, counter, &res)) *out = res;
+    if (grid_reduce(v, partials, counter, &res)) {
+        *out = res;
+        if (px.on) peer_push_scalars(px, res, extra ? *extra : 0.0);
+    }
 }
 
 // Stopping test of iteration it - 1 (its ||r||^2 = red[1], global after the allreduce) and, unless it fires,
 // p = z + (rho / rho_prev) p  (it == 1: p = z).  only_check = 1: the test alone (after the last iteration).
-__global__ void update_p_kernel(const double* __restrict__ z, double* __restrict__ p, int64_t n, const double* red,
+// Peer mode: (rho, ||r||^2) are combined from the ranks' pushes here (pa), and every thread stores its entries of p
+// into ALL ranks' replicated search direction (pv.p_full) -- the allgather is part of this kernel; the last block to
+// finish raises channel PEER_CH_P (pp).
+__global__ void update_p_kernel(const double* __restrict__ z, double* __restrict__ p, int64_t n, double* red,
                                 const double* red_test, PcgState* state, double atol2, int64_t it, int only_check,
-                                double* __restrict__ hist) {
+                                double* __restrict__ hist, const PeerXchg pa, const PeerXchg pp, int64_t row0) {
     const bool was_frozen = state->frozen != 0;
-    const double rr = red_test[1];
+    if (was_frozen) return;   // before any wait: the producers skipped their pushes, on every rank alike
+    __shared__ double s_rho, s_rr;
+    if (threadIdx.x == 0) {
+        if (pa.on) peer_sum_scalars(pa, s_rho, s_rr);
+        else { s_rho = red[0]; s_rr = red_test[1]; }
+    }
+    __syncthreads();
+    const double rho = s_rho;
+    const double rr = s_rr;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !only_check) red[6] = rho;
     const bool test = it > 1;  // nothing to test before the first update
     const bool fire = test && (!(rr == rr) || rr <= atol2);
     if (blockIdx.x == 0 && threadIdx.x == 0 && !was_frozen && test) {
@@ -94,19 +141,42 @@ __global__ void update_p_kernel(const double* __restrict__ z, double* __restrict
             state->frozen = 1;
         }
     }
-    if (was_frozen || fire || only_check) return;
-    const double beta = (it == 1) ? 0.0 : (red[0] / red[3]);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        p[i] = (it == 1) ? z[i] : fma(beta, p[i], z[i]);
+    if (fire || only_check) return;
+    const double beta = (it == 1) ? 0.0 : (rho / red[3]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (it == 1) ? z[i] : fma(beta, p[i], z[i]);
+        p[i] = v;
+        if (pp.on)
+            for (int r = 0; r < pp.pv.world; ++r)
+                if (r != pp.pv.rank) pp.pv.p_full(r)[row0 + i] = v;
+    }
+    if (pp.on) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned* cnt = pp.pv.counter(0);
+            const unsigned done = atomicAdd(cnt, 1u);
+            if (done == gridDim.x - 1) {
+                *cnt = 0u;
+                peer_signal_all(pp.pv, PEER_CH_P, pp.epoch);
+            }
+        }
+    }
 }
 
 // alpha = rho / (p.q); x += alpha p; r -= alpha q; red[1] = sum r^2 (local); red[3] = rho
 __global__ void update_xr_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                                  const double* __restrict__ q, int64_t n, double* red, const PcgState* state,
-                                 double* partials, unsigned* counter) {
+                                 double* partials, unsigned* counter, const PeerXchg pb) {
     if (state->frozen) return;
-    const double rho = red[0];
-    const double alpha = rho / red[2];
+    __shared__ double s_pq;
+    if (threadIdx.x == 0) {
+        if (pb.on) { double dummy; peer_sum_scalars(pb, s_pq, dummy); }
+        else s_pq = red[2];
+    }
+    __syncthreads();
+    const double rho = red[6];
+    const double alpha = rho / s_pq;
     double v = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         x[i] = fma(alpha, p[i], x[i]);
@@ -217,7 +287,9 @@ int mlffpc_dot(mlffpc_ctx* ctx, const double* a, const double* b, int64_t n, dou
     MLFFPC_REQUIRE(ctx && a && b && out_host && n >= 0, "dot: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
     unsigned* counter = (unsigned*)(ctx->scal + S_COUNTER);
-    dot_kernel<<<vec_grid(n), VEC_THREADS, 0, s>>>(a, b, n, ctx->partials, counter, ctx->scal + S_TMP, nullptr);
+    PeerXchg off;
+    off.on = 0;
+    dot_kernel<<<vec_grid(n), VEC_THREADS, 0, s>>>(a, b, n, ctx->partials, counter, ctx->scal + S_TMP, nullptr, off, nullptr);
     MLFFPC_LAUNCH_CHECK();
     MLFFPC_TRY(comm_allreduce_sum(ctx->comm, ctx->scal + S_TMP, 1, s));
     MLFFPC_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->scal + S_TMP, 8, cudaMemcpyDeviceToHost, s));
@@ -261,8 +333,26 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     double* r = (double*)(base + w.off_r);
     double* z = (double*)(base + w.off_z);
     double* q = (double*)(base + w.off_q);
-    double* p_full = (double*)(base + w.off_p);
+    // peer mode: the replicated search direction lives in this rank's peer buffer, where the other ranks' p-update
+    // kernels store their slices directly
+    const bool peer = peer_on(ctx);
+    Peer* pr = peer ? ctx->peer : nullptr;
+    double* p_full = peer ? (double*)((char*)pr->local + pr->view.lay.off_p) : (double*)(base + w.off_p);
     double* p = p_full + row0;
+    PeerXchg off;
+    off.on = 0;
+    auto xchg = [&](int ch) -> PeerXchg {  // one round of a fused exchange: same epoch / slot for producer and consumer
+        PeerXchg x;
+        x.on = 0;
+        if (peer) {
+            x.pv = pr->view;
+            x.on = 1;
+            x.ch = ch;
+            x.parity = (int)(pr->uses[ch]++ & 1);
+            x.epoch = ++pr->epoch;
+        }
+        return x;
+    };
     double* xg = (world > 1) ? (double*)(base + w.off_xg) : nullptr;
     double* u = (double*)(base + w.off_u);
     PcgState* state = (PcgState*)(base + w.off_state);
@@ -309,7 +399,7 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     if (!resume) MLFFPC_CUDA(cudaMemsetAsync(base + w.off_state, 0, 256, s));
     else MLFFPC_CUDA(cudaMemsetAsync(state, 0, sizeof(PcgState), s));
     double bb = 0.0;
-    dot_kernel<<<g, VEC_THREADS, 0, s>>>(b, b, nl, ctx->partials, counter, sc + S_TMP, nullptr);
+    dot_kernel<<<g, VEC_THREADS, 0, s>>>(b, b, nl, ctx->partials, counter, sc + S_TMP, nullptr, off, nullptr);
     MLFFPC_LAUNCH_CHECK();
     MLFFPC_TRY(comm_allreduce_sum(ctx->comm, sc + S_TMP, 1, s));
     MLFFPC_TRY(host_scalar(sc + S_TMP, &bb));
@@ -327,7 +417,8 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     }
     const double atol = (bnrm2 == 0.0) ? tol : tol * bnrm2;
     const double atol2 = atol * atol;
-    if (world > 1 && !resume) MLFFPC_CUDA(cudaMemsetAsync(p_full, 0, (size_t)world * w.n_pad * 8, s));
+    // (peer mode: the buffer was zeroed when it was created, and a faster rank may already be storing into it)
+    if (world > 1 && !resume && !peer) MLFFPC_CUDA(cudaMemsetAsync(p_full, 0, (size_t)world * w.n_pad * 8, s));
 
     // batches of iterations; the state of batch i is read while batch i + 1 runs
     constexpr int BATCH = 4, SLOTS = 2;
@@ -360,19 +451,22 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
             MLFFPC_CUDA(cudaMemcpyAsync(z, r, nl * 8, cudaMemcpyDeviceToDevice, s));
         }
         MLFFPC_CUDA(cudaEventRecord(ev_iter(slot, i, 1), s));
-        dot_kernel<<<g, VEC_THREADS, 0, s>>>(r, z, nl, ctx->partials, counter, red + 0, state);
+        const PeerXchg xa = xchg(PEER_CH_SCAL_A), xp = xchg(PEER_CH_P), xb = xchg(PEER_CH_SCAL_B);
+        dot_kernel<<<g, VEC_THREADS, 0, s>>>(r, z, nl, ctx->partials, counter, red + 0, state, xa, red + 1);
         MLFFPC_LAUNCH_CHECK();
-        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, red, 2, s));  // (rho, ||r||^2 of the previous update)
-        update_p_kernel<<<g, VEC_THREADS, 0, s>>>(z, p, nl, red, red, state, atol2, it, 0, it - 1 < w.hist_len ? hist : nullptr);
+        if (!peer) MLFFPC_TRY(comm_allreduce_sum(ctx->comm, red, 2, s));  // (rho, ||r||^2 of the previous update)
+        update_p_kernel<<<g, VEC_THREADS, 0, s>>>(z, p, nl, red, red, state, atol2, it, 0, it - 1 < w.hist_len ? hist : nullptr,
+                                                  xa, xp, row0);
         MLFFPC_LAUNCH_CHECK();
-        if (world > 1) MLFFPC_TRY(comm_allgather(ctx->comm, p, p_full, w.n_pad * 8, s));
+        if (peer) MLFFPC_TRY(peer_wait(ctx, PEER_CH_P, xp.epoch, &state->frozen, s));
+        else if (world > 1) MLFFPC_TRY(comm_allgather(ctx->comm, p, p_full, w.n_pad * 8, s));
         MLFFPC_CUDA(cudaEventRecord(ev_iter(slot, i, 2), s));
         MLFFPC_TRY(A.apply(p_full, q, s));
         MLFFPC_CUDA(cudaEventRecord(ev_iter(slot, i, 3), s));
-        dot_kernel<<<g, VEC_THREADS, 0, s>>>(p, q, nl, ctx->partials, counter, red + 2, state);
+        dot_kernel<<<g, VEC_THREADS, 0, s>>>(p, q, nl, ctx->partials, counter, red + 2, state, xb, nullptr);
         MLFFPC_LAUNCH_CHECK();
-        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, red + 2, 1, s));
-        update_xr_kernel<<<g, VEC_THREADS, 0, s>>>(x, r, p, q, nl, red, state, ctx->partials, counter);
+        if (!peer) MLFFPC_TRY(comm_allreduce_sum(ctx->comm, red + 2, 1, s));
+        update_xr_kernel<<<g, VEC_THREADS, 0, s>>>(x, r, p, q, nl, red, state, ctx->partials, counter, xb);
         MLFFPC_LAUNCH_CHECK();
         return MLFFPC_OK;
     };
@@ -381,7 +475,8 @@ int mlffpc_pcg(mlffpc_ctx* ctx, const double* K_local, int64_t ld_k, double lam,
     auto launch_check = [&](int64_t it_next) -> int {
         MLFFPC_CUDA(cudaMemcpyAsync(red + 4, red, 16, cudaMemcpyDeviceToDevice, s));
         MLFFPC_TRY(comm_allreduce_sum(ctx->comm, red + 4, 2, s));
-        update_p_kernel<<<1, 32, 0, s>>>(z, p, nl, red, red + 4, state, atol2, it_next, 1, it_next - 1 < w.hist_len ? hist : nullptr);
+        update_p_kernel<<<1, 32, 0, s>>>(z, p, nl, red, red + 4, state, atol2, it_next, 1, it_next - 1 < w.hist_len ? hist : nullptr,
+                                         off, off, row0);
         MLFFPC_LAUNCH_CHECK();
         return MLFFPC_OK;
     };

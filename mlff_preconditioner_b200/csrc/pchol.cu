@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace mlffpc {
 
@@ -359,6 +360,7 @@ __global__ void pchol_gather_cand_rows_kernel(const double* __restrict__ Lt, int
 // The host launches LA_CHUNK steps, then reads the 64-byte state once.
 constexpr int LA_MSG = 4 + LA_C;   // candidate (val, pos, idx, pad) + at most LA_C entries of its factor row
 constexpr int LA_CHUNK = 8;
+static_assert(LA_MSG <= PEER_MSG_DOUBLES, "peer message slot too small");
 
 struct LaState {
     int stalled;        // 1: a step could not run (panel miss or non-PSD pivot); cleared by the host
@@ -386,9 +388,12 @@ __device__ __forceinline__ void la_apply_pending(LaState* st, int64_t* index_col
     }
 }
 
+// peer mode (pv_on): the message goes straight into every rank's slot `parity` and channel PEER_CH_MSG is raised --
+// no collective call between the two kernels of a step
 __global__ void pchol_la_prepare_kernel(const Cand* __restrict__ partials, int count, const double* __restrict__ Lt,
                                         int64_t ld, int64_t m0, int64_t m, int64_t row0, int64_t* index_columns,
-                                        int32_t* pos, LaState* st, double* __restrict__ send) {
+                                        int32_t* pos, LaState* st, double* __restrict__ send, const PeerView pv,
+                                        int pv_on, int parity, uint64_t epoch) {
     if (st->stalled) return;
     __shared__ Cand sm[40];
     if (threadIdx.x == 0) la_apply_pending(st, index_columns, pos);
@@ -403,6 +408,17 @@ __global__ void pchol_la_prepare_kernel(const Cand* __restrict__ partials, int c
     const int64_t g = (int64_t)best.idx;
     for (int64_t t = m0 + threadIdx.x; t < m; t += blockDim.x)
         send[4 + (t - m0)] = (g >= 0) ? Lt[t * ld + (g - row0)] : 0.0;
+    if (pv_on) {
+        __syncthreads();
+        const int len = 4 + (int)(m - m0);
+        for (int r = 0; r < pv.world; ++r) {
+            double* dst = pv.msg(r, parity, pv.rank);
+            for (int t = threadIdx.x; t < len; t += blockDim.x) dst[t] = send[t];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) peer_signal_all(pv, PEER_CH_MSG, epoch);
+    }
 }
 
 __global__ void pchol_la_flush_kernel(LaState* st, int64_t* index_columns, int32_t* pos) {
@@ -414,7 +430,8 @@ __global__ void __launch_bounds__(PCHOL_THREADS)
 pchol_la_update_kernel(double* __restrict__ Lt, int64_t ld, int64_t m0, int64_t m, int64_t n_local, int64_t row0,
                        const double* __restrict__ panel, int64_t ld_panel, const double* __restrict__ gathered, int world,
                        const int32_t* __restrict__ cslot, double* __restrict__ diag, const int32_t* __restrict__ pos,
-                       const int64_t* __restrict__ index_columns, Cand* partials, LaState* st) {
+                       const int64_t* __restrict__ index_columns, Cand* partials, LaState* st, const PeerView pv,
+                       int pv_on, int parity, uint64_t epoch) {
     constexpr int COLS = PCHOL_THREADS / MSPLIT;
     __shared__ double red[MSPLIT][COLS];
     __shared__ Cand sm[40];
@@ -422,13 +439,19 @@ pchol_la_update_kernel(double* __restrict__ Lt, int64_t ld, int64_t m0, int64_t 
     __shared__ double s_val;
     __shared__ long long s_pi;
     __shared__ int s_slot, s_rank, s_stalled;
+    // the ranks' messages: the allgather buffer, or (peer mode) this rank's message slots once every rank has raised
+    // the channel -- skipped while stalled, when no rank has pushed
+    const int64_t msg_stride = pv_on ? PEER_MSG_DOUBLES : LA_MSG;
+    if (pv_on) gathered = pv.msg(pv.rank, parity, 0);
     if (threadIdx.x == 0) {
         s_stalled = st->stalled;
+        if (pv_on && !s_stalled) peer_wait_all(pv, PEER_CH_MSG, epoch);
         double v = -1e300, p = 1e300, i = -1.0;
         int wr = 0;
-        for (int r = 0; r < world; ++r) {
-            const double* c = gathered + (int64_t)r * LA_MSG;
-            if (cand_better(c[0], c[1], v, p)) { v = c[0]; p = c[1]; i = c[2]; wr = r; }
+        for (int r = 0; r < world && !s_stalled; ++r) {
+            const double* c = gathered + (int64_t)r * msg_stride;
+            const double c0 = peer_ld(c), c1 = peer_ld(c + 1), c2 = peer_ld(c + 2);
+            if (cand_better(c0, c1, v, p)) { v = c0; p = c1; i = c2; wr = r; }
         }
         s_val = v; s_pi = (long long)i; s_rank = wr;
         s_slot = (i >= 0.0) ? cslot[(int64_t)i] : -1;
@@ -446,7 +469,7 @@ pchol_la_update_kernel(double* __restrict__ Lt, int64_t ld, int64_t m0, int64_t 
         }
         return;
     }
-    for (int t = threadIdx.x; t < (int)(m - m0); t += blockDim.x) lrow[t] = gathered[(int64_t)s_rank * LA_MSG + 4 + t];
+    for (int t = threadIdx.x; t < (int)(m - m0); t += blockDim.x) lrow[t] = peer_ld(gathered + (int64_t)s_rank * msg_stride + 4 + t);
     __syncthreads();
     const double piv = sqrt(s_val);
     const int tc = threadIdx.x % COLS, ts = threadIdx.x / COLS;
@@ -619,6 +642,10 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
         double* send = (double*)(base + w.off_send);
         double* recv = (world > 1) ? (double*)(base + w.off_recv) : send;
         LaState* h_st = (LaState*)(ctx->h_scal + 24);  // pinned; 64 bytes
+        const int pv_on = (peer_on(ctx) && ctx->peer_pivots) ? 1 : 0;
+        PeerView pv;
+        if (pv_on) pv = ctx->peer->view;
+        else memset(&pv, 0, sizeof(pv));
         do {
             LaState init;
             memset(&init, 0, sizeof(init));
@@ -637,14 +664,19 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
                 const int64_t chunk_end = (m + LA_CHUNK < k) ? (m + LA_CHUNK) : k;
                 for (int64_t mm = m; mm < chunk_end; ++mm) {
                     pw.step(mm);
-                    pchol_la_prepare_kernel<<<1, 256, 0, s>>>(partials, prev_parts, Lt, ld, m0, mm, row0, index_columns, pos, st, send);
-                    if (world > 1) {
+                    int parity = 0;
+                    uint64_t epoch = 0;
+                    if (pv_on) { parity = (int)(ctx->peer->uses[PEER_CH_MSG]++ & 1); epoch = ++ctx->peer->epoch; }
+                    pchol_la_prepare_kernel<<<1, 256, 0, s>>>(partials, prev_parts, Lt, ld, m0, mm, row0, index_columns, pos, st, send,
+                                                              pv, pv_on, parity, epoch);
+                    if (world > 1 && !pv_on) {
                         status = comm_allgather(ctx->comm, send, recv, LA_MSG * sizeof(double), s);
                         if (status != MLFFPC_OK) break;
                     }
                     // One thread per row, always: a step applies at most LA_C factor columns, and the candidate partials
                     // must keep ONE layout -- a stalled (no-op) launch leaves the previous step's partials in place.
-                    pchol_la_update_kernel<1><<<(unsigned)n_part, PCHOL_THREADS, 0, s>>>(Lt, ld, m0, mm, nl, row0, panel, nl, recv, world, cslot, diag, pos, index_columns, partials, st);
+                    pchol_la_update_kernel<1><<<(unsigned)n_part, PCHOL_THREADS, 0, s>>>(Lt, ld, m0, mm, nl, row0, panel, nl, recv, world, cslot, diag, pos, index_columns, partials, st,
+                                                                                         pv, pv_on, parity, epoch);
                     g_launches += 2;
                     if (step_ms_host) cudaEventRecord(ev[(size_t)mm + 1], s);
                 }

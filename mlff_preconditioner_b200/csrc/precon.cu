@@ -42,6 +42,14 @@ static int factor_times_vec(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t
     return launch_gemv_rows(T, k, nl, ld, r, w, 1.0, 0.0, 0, s, false);
 }
 
+// sum of a k-vector over the ranks: one small peer-memory kernel (push, flag, wait, rank-ordered sum) when the peer
+// buffers are mapped, else ncclAllReduce
+static int kvec_allreduce(mlffpc_ctx* ctx, double* w, int64_t k, cudaStream_t s) {
+    if (ctx->comm.world <= 1) return MLFFPC_OK;
+    if (peer_on(ctx) && ctx->peer_kvec && k <= peer_kmax(ctx)) return peer_allreduce_kvec(ctx, w, k, s);
+    return comm_allreduce_sum(ctx->comm, w, (size_t)k, s);
+}
+
 // u: device scratch of 4 k + 8 doubles.  Mk == NULL: Woodbury form z = sign (r - T^T T r) / lam.
 // Mk != NULL: T holds an orthonormal basis Q^T of range(L) and Mk = (Q^T L L^T Q + lam I)^{-1}:
 //   z = sign ( (r - Q (Q^T r)) / lam + Q Mk (Q^T r) ).
@@ -59,7 +67,7 @@ int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double
         double* g1 = u + ko;       // w - E w
         double* g2 = u + 2 * ko;   // Mk w
         MLFFPC_TRY(factor_times_vec(ctx, T, k, nl, ld, r, w, s));
-        MLFFPC_TRY(comm_allreduce_sum(ctx->comm, w, (size_t)k, s));
+        MLFFPC_TRY(kvec_allreduce(ctx, w, k, s));
         MLFFPC_TRY(launch_gemv_rows(E, k, k, k, w, g1, -1.0, 1.0, 0, s, false));
         MLFFPC_TRY(launch_gemv_rows(Mk, k, k, k, w, g2, 1.0, 0.0, 0, s, false));
         return launch_tgemv_cols(T, k, nl, ld, g1, z, 1, r, sign / lam, ctx->num_sms, s, false, ctx->tgemv_msplit, g2, sign);
@@ -79,7 +87,7 @@ int precon_apply(mlffpc_ctx* ctx, const double* T, int64_t k, int64_t ld, double
     } else {
         MLFFPC_TRY(factor_times_vec(ctx, T, k, nl, ld, r, u, s));
     }
-    MLFFPC_TRY(comm_allreduce_sum(ctx->comm, u, (size_t)k, s));
+    MLFFPC_TRY(kvec_allreduce(ctx, u, k, s));
     if (Mk && ctx->precon_reorth && ctx->reorth_scratch) {
         // Orthonormal form with the complement projected twice ("twice is enough"): Qt Qt^T = I + E with
         // |E| ~ 1e-16 sqrt(n), and (I - Qt^T Qt) a / lam leaks E / lam ~ 1e-4 of a range vector back into the

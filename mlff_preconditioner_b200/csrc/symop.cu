@@ -291,7 +291,9 @@ int symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full, doubl
         return symv_tile_tma(ctx, Ksym + t.off, 0, t.nr, t.nc, 1, 1, x_full, x_full, wt, y_local, nullptr, x_full,
                              alpha, shift, s);
     }
-    double* yp = partial_out ? partial_out : (double*)(base + w.off_yp);
+    // with mapped peer buffers the partial products are written where the other ranks can pull them
+    const bool peer = !partial_out && peer_on(ctx) && ctx->comm.world == W;
+    double* yp = partial_out ? partial_out : (peer ? peer_yp_local(ctx) : (double*)(base + w.off_yp));
     MLFFPC_CUDA(cudaMemsetAsync(yp, 0, (size_t)W * w.n_pad * 8, s));
     for (const auto& t : tiles) {
         const double* xr = x_full + t.i_pt0 * di;
@@ -301,9 +303,10 @@ int symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full, doubl
     }
     if (partial_out) return MLFFPC_OK;
     MLFFPC_REQUIRE(ctx->comm.world == W, "symop_apply: the tile layout (%d ranks) needs a communicator of that size", W);
+    const int64_t nl = ctx->n_local();
+    if (peer) return symop_finish_peer(ctx, x_full + ctx->row0(), y_local, nl, ctx->row0(), alpha, shift, s);
     double* q = (double*)(base + w.off_q);
     MLFFPC_TRY(comm_reduce_scatter_sum(ctx->comm, yp, q, (size_t)w.n_pad, s));
-    const int64_t nl = ctx->n_local();
     symop_finish_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, s>>>(q, x_full + ctx->row0(), y_local, nl, alpha, shift);
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;

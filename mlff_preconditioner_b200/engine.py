@@ -154,6 +154,37 @@ class Engine(object):
             self.ctx, self.M, self.N, self.S, _ptr(self._R_desc), _ptr(self._R_d_desc), _ptr(self._dperms),
             _ptr(self._aperms), self.sig, self.pt0, self.pt1, _ptr(self._geo_ws), nbytes.value, self._stream()))
         self._ws_cache = {}
+        self.peer_collectives = False
+        if world > 1:
+            self._peer_setup()
+
+    def _peer_setup(self, k_max=65536):
+        """Map every rank's communication buffer (CUDA IPC) so the inner loops can use NVLink peer stores / loads
+        instead of one library collective per step (include/mlffpc.h, csrc/peer.cuh).  All ranks take the same
+        decision: if any rank cannot export or import, every rank falls back to NCCL.  MLFFPC_PEER=0 disables it."""
+        import os
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() != self.world:
+            return
+        want = os.environ.get('MLFFPC_PEER', '1') != '0'
+        handle = (ctypes.c_char * 64)()
+        ok = 1 if (want and self.lib.mlffpc_peer_export(self.ctx, int(k_max), handle) == 0) else 0
+        dev = self.device if dist.get_backend() == 'nccl' else torch.device('cpu')
+        mine = torch.tensor(list(handle.raw) + [ok], dtype=torch.uint8, device=dev)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine)
+        rows = [bytes(t.cpu().tolist()) for t in gathered]
+        ok_all = all(r[64] == 1 for r in rows)
+        if ok_all:
+            blob = b''.join(r[:64] for r in rows)
+            ok_all = self.lib.mlffpc_peer_import(self.ctx, blob, self.world) == 0
+        flag = torch.tensor([1 if ok_all else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            self.lib.mlffpc_peer_disable(self.ctx)
+            return
+        self.peer_collectives = True
 
     # ---- plumbing -------------------------------------------------------------------------
     def _stream(self):

@@ -293,6 +293,7 @@ class Iterative(object):
             self.timings['resid_hist_rel'] = res[5] / bnrm2
         sync()
         total_time_cg = timeit.default_timer() - tic_start
+        self.timings['peer_collectives'] = bool(getattr(eng, 'peer_collectives', False))
         self.timings.update(cg=total_time_cg, preconditioner=total_time_preconditioner, cg_iters=iters, k=k_rank,
                             pcg_stats=dict(eng.last_pcg_stats))
         return x, iters, resid, info, inducing_pts_idxs, info_cholesky, total_time_preconditioner, total_time_cg

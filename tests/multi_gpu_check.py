@@ -80,15 +80,21 @@ def main():
     gath = [torch.empty_like(E) for _ in range(world)]
     dist.all_gather(gath, E)
     assert all(torch.equal(g_, gath[0]) for g_ in gath), 'defect matrix differs between ranks'
-    errE = float((E - E_ref).abs().max())
+    # the defect belongs to THIS factor (the sharded Gram sums differ from the single-GPU ones in the last bits, so Qt
+    # and with it E differ at the 1e-16 level): gather the sharded Qt and measure its defect on one GPU
+    parts = [None] * world
+    dist.all_gather_object(parts, Qt.cpu())
+    Q_full = torch.cat(parts, dim=1).to('cuda')
+    errE = float((E - ref.gram_defect(Q_full)).abs().max())
     errQ = float((Qt - Qt_ref[:, sl]).abs().max())
+    del Q_full, parts
     z = eng.precon_apply(Qt, lam, 1.0, a[sl].contiguous(), Mk=Mk, E=E)
     z_ref = ref.precon_apply(Qt_ref, lam, 1.0, a, Mk=Mk_ref, E=E_ref)
     err = float((z - z_ref[sl]).norm() / z_ref[sl].norm())
     if rank == 0:
         print('  projected form sharded vs single: max |dE| %.2e (|E| max %.2e), max |dQ| %.2e, apply rel diff %.2e'
               % (errE, float(E_ref.abs().max()), errQ, err), flush=True)
-    assert errE < 1e-16 and err < (1e-3 if big else 1e-8), (errE, err)
+    assert errE < 2e-17 and err < (1e-3 if big else 1e-8), (errE, err)
     del Lt2, Lt2_ref, Qt, Mk, E, Qt_ref, Mk_ref, E_ref
 
     # matvecs
@@ -158,7 +164,8 @@ def main():
     full = allgather_rows(eng, a[sl].contiguous())
     assert torch.equal(full, a)
     dist.barrier()
-    print('MULTI_GPU_CHECK OK rank %d/%d n=%d n_local=%d' % (rank, world, n, eng.n_local), flush=True)
+    print('MULTI_GPU_CHECK OK rank %d/%d n=%d n_local=%d peer_collectives=%s' % (rank, world, n, eng.n_local,
+                                                                                eng.peer_collectives), flush=True)
     dist.destroy_process_group()
 
 
