@@ -94,7 +94,10 @@ def main():
     if rank == 0:
         print('  projected form sharded vs single: max |dE| %.2e (|E| max %.2e), max |dQ| %.2e, apply rel diff %.2e'
               % (errE, float(E_ref.abs().max()), errQ, err), flush=True)
-    assert errE < 2e-17 and err < (1e-3 if big else 1e-8), (errE, err)
+    # the two defects fold the same products in different 16-column groupings (rank 1's columns do not start on a
+    # k-tile boundary): they may differ by the rounding inside the k-tile products, eps * 16/n per rounding
+    tolE = 1.1e-16 * (16.0 / n) * 4 * np.sqrt(n)
+    assert errE < tolE and err < (1e-3 if big else 1e-8), (errE, tolE, err)
     del Lt2, Lt2_ref, Qt, Mk, E, Qt_ref, Mk_ref, E_ref
 
     # matvecs
