@@ -134,6 +134,8 @@ int mlffpc_symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full
  *   "gram_mode"       [1]  Gram matrices (mlffpc_syrk_rows) with (hi, lo) accumulation of the k-tile products;
  *                          0 = one running fp64 sum per entry (the round-1 kernel: 188 instead of the reference's 119
  *                          CG iterations on BASELINE.json configs[0])
+ *   "pairs_kernel"    [2]  pair stage of the matrix-free operator / prediction: 2 = 128 x 64 tiles with a cp.async ring,
+ *                          1 = the round-1 kernel (64 x 64 tiles, synchronous staging)
  *   "peer_kvec", "peer_pivots" [1]  use the mapped peer buffers for the apply's k-vector sum / the pivot-step message
  *   "tma_rows"        [1]  "T r" of the preconditioner apply on the TMA-fed row-strip kernel (csrc/symtma.cu); 0 = the
  *                          register-staged 4-row GEMV of round 1

@@ -115,6 +115,143 @@ mv_pairs_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __restr
     }
 }
 
+// Second-generation pair kernel: 128 queries x 64 training rows per CTA, 8 x 4 pairs per thread, descriptor chunks of
+// 16 staged by cp.async into a 3-stage ring (transposed to [d][row] so that a thread's 8 query values and its 2 x 2
+// training values are 128-bit shared loads).  Per descriptor and thread: 8 LDS.128 for 96 FP64 instructions (the first
+// kernel: 12 LDS.64 for 48, and no overlap of the global loads with the arithmetic -- with D = 36 its three chunks
+// were latency-, not pipe-bound).  Same arithmetic per pair as mv_pairs_kernel, same outputs.
+constexpr int P2_TI = 128, P2_TJ = 64, P2_DC = 16, P2_STAGES = 3, P2_THREADS = 256;
+constexpr int P2_QS = P2_TI + 2, P2_JS = P2_TJ + 2;                      // padded row lengths (even: 16-byte aligned pairs)
+constexpr int P2_STAGE = P2_DC * (P2_QS + 2 * P2_JS);                    // doubles per stage
+constexpr size_t P2_SMEM = (size_t)P2_STAGES * P2_STAGE * sizeof(double);
+
+__device__ __forceinline__ void p2_cp8(void* dst, const void* src, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = ok ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz));
+}
+
+__global__ void __launch_bounds__(P2_THREADS, 1)
+mv_pairs2_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __restrict__ Bmat, int64_t ldb,
+                 int64_t MS, int D, double q, double pref, double* __restrict__ Cmat, int64_t ldc,
+                 double* __restrict__ Epart, int n_epart) {
+    extern __shared__ double p2_smem[];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int64_t i0 = (int64_t)blockIdx.y * P2_TI, j0 = (int64_t)blockIdx.x * P2_TJ;
+    double s2[8][4], tt[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) s2[a][b] = tt[a][b] = 0.0;
+
+    const int nchunks = (D + P2_DC - 1) / P2_DC;
+    auto load_stage = [&](int stage, int c) {
+        double* xq = p2_smem + (size_t)stage * P2_STAGE;
+        double* xj = xq + P2_DC * P2_QS;
+        double* bj = xj + P2_DC * P2_JS;
+        const int d0 = c * P2_DC;
+        // queries: 128 rows x 16 d; a thread copies 8 elements (row = e / 16 keeps the global reads of a warp in rows of 16)
+        for (int e = tid; e < P2_TI * P2_DC; e += P2_THREADS) {
+            const int r = e / P2_DC, d = e % P2_DC;
+            const bool ok = (i0 + r < Ml) && (d0 + d < D);
+            p2_cp8(xq + d * P2_QS + r, ok ? (Xq + (i0 + r) * D + d0 + d) : Xq, ok);
+        }
+        for (int e = tid; e < P2_TJ * P2_DC; e += P2_THREADS) {
+            const int r = e / P2_DC, d = e % P2_DC;
+            const bool ok = (j0 + r < MS) && (d0 + d < D);
+            p2_cp8(xj + d * P2_JS + r, ok ? (Bmat + (j0 + r) * ldb + d0 + d) : Bmat, ok);
+            p2_cp8(bj + d * P2_JS + r, ok ? (Bmat + (MS + j0 + r) * ldb + d0 + d) : Bmat, ok);
+        }
+    };
+#pragma unroll
+    for (int st = 0; st < P2_STAGES - 1; ++st) {
+        if (st < nchunks) load_stage(st, st);
+        asm volatile("cp.async.commit_group;");
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(P2_STAGES - 2));
+        __syncthreads();
+        {
+            const int nc = c + P2_STAGES - 1;
+            if (nc < nchunks) load_stage(nc % P2_STAGES, nc);
+            asm volatile("cp.async.commit_group;");
+        }
+        const double* xq = p2_smem + (size_t)(c % P2_STAGES) * P2_STAGE;
+        const double* xj = xq + P2_DC * P2_QS;
+        const double* bj = xj + P2_DC * P2_JS;
+#pragma unroll 4
+        for (int dd = 0; dd < P2_DC; ++dd) {
+            double xi[8], xv[4], bv[4];
+            const double2* q2 = reinterpret_cast<const double2*>(xq + dd * P2_QS + ty * 8);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { const double2 t = q2[a]; xi[2 * a] = t.x; xi[2 * a + 1] = t.y; }
+            {
+                const double2 t0 = *reinterpret_cast<const double2*>(xj + dd * P2_JS + 2 * tx);
+                const double2 t1 = *reinterpret_cast<const double2*>(xj + dd * P2_JS + 32 + 2 * tx);
+                xv[0] = t0.x; xv[1] = t0.y; xv[2] = t1.x; xv[3] = t1.y;
+                const double2 u0 = *reinterpret_cast<const double2*>(bj + dd * P2_JS + 2 * tx);
+                const double2 u1 = *reinterpret_cast<const double2*>(bj + dd * P2_JS + 32 + 2 * tx);
+                bv[0] = u0.x; bv[1] = u0.y; bv[2] = u1.x; bv[3] = u1.y;
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const double dl = xi[a] - xv[b];
+                    s2[a][b] = fma(dl, dl, s2[a][b]);
+                    tt[a][b] = fma(dl, bv[b], tt[a][b]);
+                }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;");
+    const double q2c = q * q;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int64_t i = i0 + ty * 8 + a;
+        double esum = 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int64_t j = j0 + (b >> 1) * 32 + 2 * tx + (b & 1);
+            if (i >= Ml || j >= MS) continue;
+            const double rho = q * sqrt(s2[a][b]);
+            const double e = pref * exp(-rho);
+            const double c2 = e * (1.0 + rho);
+            Cmat[i * ldc + j] = e * q2c * tt[a][b];
+            Cmat[i * ldc + MS + j] = c2;
+            esum = fma(c2, tt[a][b], esum);
+        }
+        if (Epart) {  // the 16 threads of a row sit in one half-warp
+            esum += __shfl_xor_sync(0xffffffffu, esum, 8);
+            esum += __shfl_xor_sync(0xffffffffu, esum, 4);
+            esum += __shfl_xor_sync(0xffffffffu, esum, 2);
+            esum += __shfl_xor_sync(0xffffffffu, esum, 1);
+            if (tx == 0 && i < Ml) Epart[i * n_epart + blockIdx.x] = esum;
+        }
+    }
+}
+
+// pair stage: the second-generation kernel unless option "pairs_kernel" = 1 selects the first one
+static int launch_pairs(mlffpc_ctx* ctx, const double* Xq, int64_t Mq, const double* Bmat, int64_t ldb, int64_t MS, int D,
+                        double q, double pref, double* Cmat, double* Epart, cudaStream_t s) {
+    if (ctx->pairs_kernel == 1) {
+        dim3 grid((unsigned)((MS + PT - 1) / PT), (unsigned)((Mq + PT - 1) / PT));
+        MLFFPC_REQUIRE(grid.y <= 65535, "pairs: too many query points for this launch shape");
+        mv_pairs_kernel<<<grid, 256, 0, s>>>(Xq, Mq, Bmat, ldb, MS, D, q, pref, Cmat, 2 * MS, Epart);
+        MLFFPC_LAUNCH_CHECK();
+        return MLFFPC_OK;
+    }
+    static_assert(P2_TJ == PT, "the energy partials are laid out per 64-column tile");
+    dim3 grid((unsigned)((MS + P2_TJ - 1) / P2_TJ), (unsigned)((Mq + P2_TI - 1) / P2_TI));
+    MLFFPC_REQUIRE(grid.y <= 65535, "pairs: too many query points for this launch shape");
+    if (!ctx->pairs2_attr) {
+        MLFFPC_CUDA(cudaFuncSetAttribute(mv_pairs2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM));
+        ctx->pairs2_attr = true;
+    }
+    mv_pairs2_kernel<<<grid, P2_THREADS, P2_SMEM, s>>>(Xq, Mq, Bmat, ldb, MS, D, q, pref, Cmat, 2 * MS, Epart, (int)grid.x);
+    MLFFPC_LAUNCH_CHECK();
+    return MLFFPC_OK;
+}
+
 // CTA per local point: G = sum of the split-K partials; f = G[i,D] x_i - G[i,:D];  y = alpha J_i^T f + shift v_local
 // R_desc / R_d_desc / v are indexed by pt0 + il (training mode: the context's tables; prediction: the query tables with
 // pt0 = 0).  Epart != NULL: E[il] = sum of the pair kernel's per-tile energy partials (fixed order).
@@ -201,10 +338,7 @@ int matvec_free(mlffpc_ctx* ctx, const double* v, double* y_local, double alpha,
     mv_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(MS, ctx->S, D, N, w.ldb, ctx->Xp, ctx->R_d_desc,
                                                                      ctx->desc_perms, ctx->pair_a, ctx->pair_b, v, nullptr, Bmat);
     MLFFPC_LAUNCH_CHECK();
-    dim3 grid((unsigned)((MS + PT - 1) / PT), (unsigned)((Ml + PT - 1) / PT));
-    MLFFPC_REQUIRE(grid.y <= 65535, "matvec_free: too many local points for this launch shape");
-    mv_pairs_kernel<<<grid, 256, 0, s>>>(ctx->R_desc + ctx->pt0 * D, Ml, Bmat, w.ldb, MS, D, q, pref, Cmat, 2 * MS, nullptr);
-    MLFFPC_LAUNCH_CHECK();
+    MLFFPC_TRY(launch_pairs(ctx, ctx->R_desc + ctx->pt0 * D, Ml, Bmat, w.ldb, MS, D, q, pref, Cmat, nullptr, s));
     MLFFPC_TRY(dgemm(false, Ml, D + 1, 2 * MS, 1.0, Cmat, 2 * MS, Bmat, w.ldb, 0.0, G, w.ldb, false, s, w.nsplit,
                      Ml * w.ldb));
     int block = 32;
@@ -296,10 +430,7 @@ int predict(mlffpc_ctx* ctx, const double* Rq_desc, const double* Rq_d_desc, int
     mv_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(MS, ctx->S, D, N, w.ldb, ctx->Xp, ctx->R_d_desc,
                                                                      ctx->desc_perms, ctx->pair_a, ctx->pair_b, v, beta, Bmat);
     MLFFPC_LAUNCH_CHECK();
-    dim3 grid((unsigned)w.ncb, (unsigned)((B + PT - 1) / PT));
-    MLFFPC_REQUIRE(grid.y <= 65535, "predict: too many query geometries in one call (%lld)", (long long)B);
-    mv_pairs_kernel<<<grid, 256, 0, s>>>(Rq_desc, B, Bmat, w.ldb, MS, D, q, pref, Cmat, 2 * MS, E_out ? Epart : nullptr);
-    MLFFPC_LAUNCH_CHECK();
+    MLFFPC_TRY(launch_pairs(ctx, Rq_desc, B, Bmat, w.ldb, MS, D, q, pref, Cmat, E_out ? Epart : nullptr, s));
     MLFFPC_TRY(dgemm(false, B, D + 1, 2 * MS, 1.0, Cmat, 2 * MS, Bmat, w.ldb, 0.0, G, w.ldb, false, s, w.nsplit, B * w.ldb));
     int block = 32;
     while (block < 3 * N && block < 256) block <<= 1;

@@ -141,8 +141,11 @@ class Iterative(object):
 
     def _choose_kernel_mode(self, task, k):
         """'assembled_sym' (symmetric tile storage in HBM, every entry read once per iteration), 'assembled'
-        (plain row block + GEMV) or 'matrix_free'.  'auto' = the symmetric storage when it fits next to the
-        preconditioner on every rank, else matrix-free (BASELINE.json north_star)."""
+        (plain row block + GEMV) or 'matrix_free'.  'auto' = matrix-free when the symmetric storage does not fit next
+        to the preconditioner on some rank (BASELINE.json north_star), otherwise whichever operator is FASTER on this
+        system: both are applied twice to a probe vector (the assembly costs tens of milliseconds) and the ranks agree
+        on the slower rank's timings.  Small descriptors favour the on-the-fly operator (cfg2: 0.5 ms vs 7.5 ms per
+        matvec), large molecules with few points the stored one (cfg1)."""
         mode = task.get('kernel_mode', 'auto')
         if mode not in ('auto', 'assembled', 'assembled_sym', 'matrix_free'):
             raise ValueError("task['kernel_mode'] must be 'auto', 'assembled', 'assembled_sym' or 'matrix_free'")
@@ -155,7 +158,30 @@ class Iterative(object):
         if eng.world > 1:  # the ranks hold different tile sets: decide together
             import torch.distributed as dist
             dist.all_reduce(fits, op=dist.ReduceOp.MIN)
-        return 'assembled_sym' if int(fits.item()) == 1 else 'matrix_free'
+        if int(fits.item()) != 1:
+            return 'matrix_free'
+        v = torch.ones(eng.world * (-(-eng.M // eng.world)) * eng.dim_i, dtype=torch.float64, device=eng.device)
+        Ksym = eng.symop_assemble()
+        times = []
+        for op in (lambda: eng.symop_apply(Ksym, v), lambda: eng.matvec_free(v)):
+            op()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            op()
+            op()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        t = torch.tensor(times, dtype=torch.float64, device=eng.device)
+        if eng.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        self.timings['auto_probe_ms'] = {'assembled_sym': float(t[0]) / 2, 'matrix_free': float(t[1]) / 2}
+        if float(t[0]) <= float(t[1]):
+            self._probe_K = Ksym   # already assembled: the solve uses it
+            return 'assembled_sym'
+        del Ksym
+        return 'matrix_free'
 
     # ------------------------------------------------------------------ device-resident solve
     def solve_device(self, task, eng, y_t, break_percentage, str_preconditioner, n_inducing_pts, x0=None,
@@ -253,7 +279,10 @@ class Iterative(object):
         if mode == 'assembled':
             self.K_local = eng.kernel_assemble(out=task.get('_K_buffer'))
         elif mode == 'assembled_sym':  # symmetric tile storage: half the bytes per matvec and per rank
-            self.K_local = eng.symop_assemble(out=task.get('_K_buffer'))
+            self.K_local = getattr(self, '_probe_K', None)
+            self._probe_K = None
+            if self.K_local is None:
+                self.K_local = eng.symop_assemble(out=task.get('_K_buffer'))
         sync()
         self.timings['assemble'] = timeit.default_timer() - t0
         self.timings['kernel_mode'] = mode

@@ -23,6 +23,7 @@ def main():
     ap.add_argument('--world', type=int, default=8)
     ap.add_argument('--kind', default='aspirin')
     ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--pairs-kernel', type=int, default=2, help='library option pairs_kernel (1 = round-1 kernel)')
     args = ap.parse_args()
     from bench import WORKLOADS, make_inputs
     from mlff_preconditioner_b200.engine import Engine
@@ -31,6 +32,7 @@ def main():
     inp = make_inputs('mf')
     eng = Engine(inp['R_desc'], inp['R_d_desc'], inp['tpl'], 10, perms=inp['perms'], rank=0, world=args.world,
                  init_comm=(lambda e: None))
+    eng.set_option('pairs_kernel', args.pairs_kernel)
     v = torch.randn(eng.n, dtype=torch.float64, device=eng.device)
     out = eng.empty(eng.n_local)
     for _ in range(2):

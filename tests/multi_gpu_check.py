@@ -160,7 +160,10 @@ def main():
         if rank == 0:
             print('  %s/%s/%s: iters sharded %d single %d, |dalpha|/|alpha| = %.2e' % (mode, variant, form, i1, i0, d), flush=True)
         assert d < (1e-2 if big else 1e-4), (mode, variant, d)   # both are tol-accurate solutions (tol 1e-3 when big)
-        assert abs(i1 - i0) <= max(1, int(0.05 * i0)), (mode, variant, i1, i0)
+        # Nystroem preconditioners rest on a Cholesky of -K_mm +- 1e-15 I (iterative_solver.py:576-583): ill-conditioned
+        # enough that the summation order of an 8-rank Gram moves the count by ~10 % (same columns, same solution)
+        band = 0.05 if variant == 'cholesky' else 0.15
+        assert abs(i1 - i0) <= max(1, int(band * i0)), (mode, variant, i1, i0)
         assert np.array_equal(out['sharded'][2], out['single'][2])
 
     # replicated-vector helper
