@@ -129,13 +129,15 @@ int mlffpc_symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full
 /* Library switches (all optional; defaults in brackets):
  *   "symmetric_gemv"  [0]  mlffpc_pcg treats K_local as the symmetric tile storage
  *   "layout_world", "layout_rank"   tile partition override (rank emulation on one GPU)
+ *   "pchol_graph"     [1]  look-ahead build: replay each chunk of 8 pivot steps as one CUDA-graph launch (the device owns the
+ *                          step counter); 0 = launch the two kernels of every step individually
  *   "pchol_lookahead" [1]  blocked pivoted Cholesky with a candidate panel (0 = plain left-looking build)
  *   "assemble_legacy" [0]  first-generation assembly kernel (one CTA per 3N x 3N block)
  *   "gram_mode"       [1]  Gram matrices (mlffpc_syrk_rows) with (hi, lo) accumulation of the k-tile products;
  *                          0 = one running fp64 sum per entry (the round-1 kernel: 188 instead of the reference's 119
  *                          CG iterations on BASELINE.json configs[0])
- *   "pairs_kernel"    [2]  pair stage of the matrix-free operator / prediction: 2 = 128 x 64 tiles with a cp.async ring,
- *                          1 = the round-1 kernel (64 x 64 tiles, synchronous staging)
+ *   "pairs_kernel"    [0]  pair stage of the matrix-free operator / prediction: 2 = 128 x 64 tiles with a cp.async ring,
+ *                          1 = the round-1 kernel (64 x 64 tiles, synchronous staging), 0 = 2 for D >= 64 else 1 (measured)
  *   "peer_kvec", "peer_pivots" [1]  use the mapped peer buffers for the apply's k-vector sum / the pivot-step message
  *   "tma_rows"        [1]  "T r" of the preconditioner apply on the TMA-fed row-strip kernel (csrc/symtma.cu); 0 = the
  *                          register-staged 4-row GEMV of round 1

@@ -117,12 +117,13 @@ struct mlffpc_ctx {
     int64_t syrk_chunk = 0;        // option "syrk_chunk": > 0 = Gram matrices by column chunks with Kahan-summed partials (diagnostics)
     int tgemv_msplit = 0;          // option "tgemv_msplit": force the row split of T^T u (1, 4, 8; 0 = auto)
     int precon_accuracy = 0;       // option "precon_accuracy": 1 = Kahan-compensated T r and T^T u (diagnostics)
+    bool pchol_graph = true;       // option "pchol_graph": replay a chunk of pivot steps as one CUDA graph when no NCCL call sits inside
     bool pchol_lookahead = true;   // option "pchol_lookahead": candidate-panel (blocked) pivoted Cholesky
     long long last_pchol_refills = 0;  // panel rebuilds of the last mlffpc_pchol_build (diagnostics)
     bool tma_attr_symv = false, tma_attr_rows = false;  // cudaFuncSetAttribute done for this context's device
     double* rows_ws = nullptr;     // scratch of the TMA row-strip GEMV (precon.cu), owned by the context
     int64_t rows_ws_len = 0;
-    int pairs_kernel = 2;          // option "pairs_kernel": 2 = 128 x 64 tiles, cp.async ring (default); 1 = the round-1 kernel
+    int pairs_kernel = 0;          // option "pairs_kernel": 0 = by descriptor length (default), 2 = 128 x 64 tiles + cp.async ring, 1 = round-1 kernel
     bool pairs2_attr = false;
     bool peer_pivots = true;       // option "peer_pivots": pivot-step message over peer memory when mapped
     bool peer_kvec = true;         // option "peer_kvec": k-vector allreduce of the apply over peer memory when mapped

@@ -250,7 +250,7 @@ int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value) {
         return MLFFPC_OK;
     }
     if (nm == "assemble_legacy") { ctx->assemble_legacy = value != 0; return MLFFPC_OK; }
-    if (nm == "pairs_kernel") { ctx->pairs_kernel = value == 1 ? 1 : 2; return MLFFPC_OK; }
+    if (nm == "pairs_kernel") { ctx->pairs_kernel = (value == 1 || value == 2) ? (int)value : 0; return MLFFPC_OK; }
     if (nm == "peer_pivots") { ctx->peer_pivots = value != 0; return MLFFPC_OK; }
     if (nm == "peer_kvec") { ctx->peer_kvec = value != 0; return MLFFPC_OK; }
     if (nm == "tma_rows") { ctx->tma_rows = value != 0 ? 1 : 0; return MLFFPC_OK; }
@@ -258,6 +258,7 @@ int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value) {
     if (nm == "gram_mode") { ctx->gram_mode = value != 0 ? 1 : 0; return MLFFPC_OK; }
     if (nm == "syrk_chunk") { ctx->syrk_chunk = value > 0 ? value : 0; return MLFFPC_OK; }
     if (nm == "precon_accuracy") { ctx->precon_accuracy = (int)value; return MLFFPC_OK; }
+    if (nm == "pchol_graph") { ctx->pchol_graph = value != 0; return MLFFPC_OK; }
     if (nm == "pchol_lookahead") { ctx->pchol_lookahead = value != 0; return MLFFPC_OK; }
     if (nm == "layout_world") {
         MLFFPC_REQUIRE(value >= 1 && value <= 1024, "set_option: layout_world out of range");

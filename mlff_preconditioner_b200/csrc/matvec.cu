@@ -233,7 +233,10 @@ mv_pairs2_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __rest
 // pair stage: the second-generation kernel unless option "pairs_kernel" = 1 selects the first one
 static int launch_pairs(mlffpc_ctx* ctx, const double* Xq, int64_t Mq, const double* Bmat, int64_t ldb, int64_t MS, int D,
                         double q, double pref, double* Cmat, double* Epart, cudaStream_t s) {
-    if (ctx->pairs_kernel == 1) {
+    // measured (profiles/r02i_mf_*): the 128 x 64 kernel wins at D = 210 (5.43 vs 5.71 ms on the cfg5 slice) and loses at
+    // D = 36 (0.526 vs 0.490 ms at cfg2, where three 16-wide chunks cannot fill its pipeline): pick by descriptor length
+    const bool first_gen = ctx->pairs_kernel == 1 || (ctx->pairs_kernel == 0 && D < 64);
+    if (first_gen) {
         dim3 grid((unsigned)((MS + PT - 1) / PT), (unsigned)((Mq + PT - 1) / PT));
         MLFFPC_REQUIRE(grid.y <= 65535, "pairs: too many query points for this launch shape");
         mv_pairs_kernel<<<grid, 256, 0, s>>>(Xq, Mq, Bmat, ldb, MS, D, q, pref, Cmat, 2 * MS, Epart);

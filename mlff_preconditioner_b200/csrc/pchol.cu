@@ -373,6 +373,16 @@ struct LaState {
     long long pend_pi;
     long long done_m;   // steps completed
     long long pad1;
+    // The device owns the loop: every launch of the two step kernels has the SAME arguments (so a chunk of steps is one
+    // CUDA-graph launch); the prepare kernel latches the step number and the peer epoch / slot for its update kernel.
+    long long k_total;  // steps to do; launches beyond it return at once
+    long long m0;       // factor columns already folded into the candidate panel (host writes it at a rebuild)
+    long long cur_m;    // step of the update kernel that follows
+    unsigned long long epoch;   // peer channel PEER_CH_MSG: last epoch used
+    unsigned long long uses;    //   ... and rounds so far (slot parity)
+    unsigned long long cur_epoch;
+    long long cur_parity;
+    long long pad2;
 };
 
 __device__ __forceinline__ void la_apply_pending(LaState* st, int64_t* index_columns, int32_t* pos) {
@@ -391,12 +401,29 @@ __device__ __forceinline__ void la_apply_pending(LaState* st, int64_t* index_col
 // peer mode (pv_on): the message goes straight into every rank's slot `parity` and channel PEER_CH_MSG is raised --
 // no collective call between the two kernels of a step
 __global__ void pchol_la_prepare_kernel(const Cand* __restrict__ partials, int count, const double* __restrict__ Lt,
-                                        int64_t ld, int64_t m0, int64_t m, int64_t row0, int64_t* index_columns,
+                                        int64_t ld, int64_t row0, int64_t* index_columns,
                                         int32_t* pos, LaState* st, double* __restrict__ send, const PeerView pv,
-                                        int pv_on, int parity, uint64_t epoch) {
+                                        int pv_on) {
     if (st->stalled) return;
+    if (st->done_m >= st->k_total) {  // surplus launch of the last chunk: tell the update kernel there is no step
+        if (threadIdx.x == 0) st->cur_m = -1;
+        return;
+    }
     __shared__ Cand sm[40];
-    if (threadIdx.x == 0) la_apply_pending(st, index_columns, pos);
+    __shared__ long long s_par;
+    __shared__ unsigned long long s_ep;
+    const int64_t m = st->done_m, m0 = st->m0;
+    if (threadIdx.x == 0) {
+        la_apply_pending(st, index_columns, pos);
+        st->cur_m = m;
+        s_ep = ++st->epoch;
+        s_par = (long long)(st->uses++ & 1ull);
+        st->cur_epoch = s_ep;
+        st->cur_parity = s_par;
+    }
+    __syncthreads();
+    const int parity = (int)s_par;
+    const uint64_t epoch = s_ep;
     double v = -1e300, p = 1e300, i = -1.0;
     for (int t = threadIdx.x; t < count; t += blockDim.x) {
         const Cand c = partials[t];
@@ -427,12 +454,18 @@ __global__ void pchol_la_flush_kernel(LaState* st, int64_t* index_columns, int32
 
 template <int MSPLIT>
 __global__ void __launch_bounds__(PCHOL_THREADS)
-pchol_la_update_kernel(double* __restrict__ Lt, int64_t ld, int64_t m0, int64_t m, int64_t n_local, int64_t row0,
+pchol_la_update_kernel(double* __restrict__ Lt, int64_t ld, int64_t n_local, int64_t row0,
                        const double* __restrict__ panel, int64_t ld_panel, const double* __restrict__ gathered, int world,
                        const int32_t* __restrict__ cslot, double* __restrict__ diag, const int32_t* __restrict__ pos,
                        const int64_t* __restrict__ index_columns, Cand* partials, LaState* st, const PeerView pv,
-                       int pv_on, int parity, uint64_t epoch) {
+                       int pv_on) {
     constexpr int COLS = PCHOL_THREADS / MSPLIT;
+    // step number, slot and epoch were latched by the prepare kernel (done_m itself is advanced by block 0 of THIS
+    // kernel, so it must not be read here); cur_m < 0: there was no step to prepare
+    const int64_t m = st->cur_m, m0 = st->m0;
+    if (m < 0) return;
+    const int parity = (int)st->cur_parity;
+    const uint64_t epoch = st->cur_epoch;
     __shared__ double red[MSPLIT][COLS];
     __shared__ Cand sm[40];
     __shared__ double lrow[LA_C];
@@ -624,7 +657,7 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
     // candidate partials: the update kernel writes one per CTA; size the scan the same way
     int64_t n_part = (nl + 255) / 256;
     std::vector<cudaEvent_t> ev;
-    if (step_ms_host) {
+    if (step_ms_host && !la) {
         ev.resize((size_t)k + 1);
         for (auto& e : ev) MLFFPC_CUDA(cudaEventCreate(&e));
         MLFFPC_CUDA(cudaEventRecord(ev[0], s));
@@ -641,15 +674,21 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
         LaState* st = (LaState*)(base + w.off_state);
         double* send = (double*)(base + w.off_send);
         double* recv = (world > 1) ? (double*)(base + w.off_recv) : send;
-        LaState* h_st = (LaState*)(ctx->h_scal + 24);  // pinned; 64 bytes
+        LaState* h_st = (LaState*)(ctx->h_scal + 24);  // pinned; sizeof(LaState) <= 160 bytes
+        long long* h_val = (long long*)(ctx->h_scal + 48);  // pinned staging for single-field updates
         const int pv_on = (peer_on(ctx) && ctx->peer_pivots) ? 1 : 0;
         PeerView pv;
         if (pv_on) pv = ctx->peer->view;
         else memset(&pv, 0, sizeof(pv));
+        cudaGraphExec_t gexec = nullptr;
+        cudaEvent_t ev_t[2] = {nullptr, nullptr};
         do {
             LaState init;
             memset(&init, 0, sizeof(init));
             init.pend_m = -1;
+            init.cur_m = -1;
+            init.k_total = k;
+            if (pv_on) { init.epoch = ctx->peer->epoch; init.uses = ctx->peer->uses[PEER_CH_MSG]; }
             *h_st = init;
             cudaError_t e = cudaMemcpyAsync(st, h_st, sizeof(LaState), cudaMemcpyHostToDevice, s);
             if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -657,39 +696,76 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
             if (n_part > MLFFPC_MAX_PARTIALS) { set_error("pchol_build: n_local too large (%lld rows)", (long long)nl); status = MLFFPC_ERR_INVALID; break; }
             pchol_scan_kernel<<<(unsigned)n_part, 256, 0, s>>>(diag, nl, row0, pos, 0, partials);
             ++g_launches;
-            prev_parts = (int)n_part;
-            // m0 = 0 with an empty panel: the first step misses by construction and builds the first panel
-            int64_t m = 0;
-            while (m < k && status == MLFFPC_OK) {
-                const int64_t chunk_end = (m + LA_CHUNK < k) ? (m + LA_CHUNK) : k;
-                for (int64_t mm = m; mm < chunk_end; ++mm) {
-                    pw.step(mm);
-                    int parity = 0;
-                    uint64_t epoch = 0;
-                    if (pv_on) { parity = (int)(ctx->peer->uses[PEER_CH_MSG]++ & 1); epoch = ++ctx->peer->epoch; }
-                    pchol_la_prepare_kernel<<<1, 256, 0, s>>>(partials, prev_parts, Lt, ld, m0, mm, row0, index_columns, pos, st, send,
-                                                              pv, pv_on, parity, epoch);
-                    if (world > 1 && !pv_on) {
-                        status = comm_allgather(ctx->comm, send, recv, LA_MSG * sizeof(double), s);
-                        if (status != MLFFPC_OK) break;
-                    }
-                    // One thread per row, always: a step applies at most LA_C factor columns, and the candidate partials
-                    // must keep ONE layout -- a stalled (no-op) launch leaves the previous step's partials in place.
-                    pchol_la_update_kernel<1><<<(unsigned)n_part, PCHOL_THREADS, 0, s>>>(Lt, ld, m0, mm, nl, row0, panel, nl, recv, world, cslot, diag, pos, index_columns, partials, st,
-                                                                                         pv, pv_on, parity, epoch);
-                    g_launches += 2;
-                    if (step_ms_host) cudaEventRecord(ev[(size_t)mm + 1], s);
+            // One chunk = LA_CHUNK steps = 2 LA_CHUNK launches with identical arguments (the device owns the step
+            // counter).  Without a library collective between the two kernels (one GPU, or peer-memory messages) the
+            // chunk is captured once and replayed as ONE graph launch; with NCCL the kernels are launched one by one.
+            auto launch_chunk = [&]() -> int {
+                for (int c = 0; c < LA_CHUNK; ++c) {
+                    pchol_la_prepare_kernel<<<1, 256, 0, s>>>(partials, (int)n_part, Lt, ld, row0, index_columns, pos, st, send, pv, pv_on);
+                    if (world > 1 && !pv_on) MLFFPC_TRY(comm_allgather(ctx->comm, send, recv, LA_MSG * sizeof(double), s));
+                    // one thread per row, always: a step applies at most LA_C factor columns, and the candidate partials
+                    // must keep ONE layout -- a stalled (no-op) launch leaves the previous step's partials in place
+                    pchol_la_update_kernel<1><<<(unsigned)n_part, PCHOL_THREADS, 0, s>>>(Lt, ld, nl, row0, panel, nl, recv, world, cslot, diag, pos,
+                                                                                         index_columns, partials, st, pv, pv_on);
                 }
-                if (status != MLFFPC_OK) break;
+                return MLFFPC_OK;
+            };
+            if ((world == 1 || pv_on) && ctx->pchol_graph) {
+                cudaGraph_t graph = nullptr;
+                e = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
+                if (e == cudaSuccess) {
+                    status = launch_chunk();
+                    e = cudaStreamEndCapture(s, &graph);
+                    if (e == cudaSuccess && status == MLFFPC_OK) e = cudaGraphInstantiate(&gexec, graph, 0);
+                    if (graph) cudaGraphDestroy(graph);
+                }
+                if (e != cudaSuccess || status != MLFFPC_OK) {  // no graph: fall back to plain launches
+                    cudaGetLastError();
+                    gexec = nullptr;
+                    status = MLFFPC_OK;
+                }
+            }
+            if (step_ms_host) {
+                e = cudaEventCreate(&ev_t[0]);
+                if (e == cudaSuccess) e = cudaEventCreate(&ev_t[1]);
+                if (e == cudaSuccess) e = cudaEventRecord(ev_t[0], s);
+                if (e != cudaSuccess) { status = cuda_fail(e, "pchol timing events", __FILE__, __LINE__); break; }
+            }
+            int64_t done = 0;
+            int tcur = 0;
+            float carry_ms = 0.f;
+            while (done < k && status == MLFFPC_OK) {
+                pw.step(done);
+                if (gexec) {
+                    e = cudaGraphLaunch(gexec, s);
+                    if (e != cudaSuccess) { status = cuda_fail(e, "pchol chunk graph", __FILE__, __LINE__); break; }
+                } else {
+                    status = launch_chunk();
+                    if (status != MLFFPC_OK) break;
+                }
+                g_launches += 2 * LA_CHUNK;
                 cudaError_t e2 = cudaMemcpyAsync(h_st, st, sizeof(LaState), cudaMemcpyDeviceToHost, s);
+                if (e2 == cudaSuccess && step_ms_host) e2 = cudaEventRecord(ev_t[tcur ^ 1], s);
                 if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s);
                 if (e2 == cudaSuccess) e2 = cudaGetLastError();
                 if (e2 != cudaSuccess) { status = cuda_fail(e2, "pchol chunk", __FILE__, __LINE__); break; }
+                const int64_t new_done = h_st->done_m;
+                if (step_ms_host) {  // the chunk's time (incl. a preceding panel rebuild), spread over the steps it completed
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, ev_t[tcur], ev_t[tcur ^ 1]);
+                    tcur ^= 1;
+                    carry_ms += ms;
+                    if (new_done > done) {
+                        for (int64_t q = done; q < new_done; ++q) step_ms_host[q] = carry_ms / (float)(new_done - done);
+                        carry_ms = 0.f;
+                    }
+                }
+                done = new_done;
                 if (h_st->flag != 0) { h_flag_la = h_st->flag; break; }
-                if (!h_st->stalled) { m = chunk_end; continue; }
+                if (!h_st->stalled) continue;
                 // (2b) panel rebuild at the stalled step: top rows by residual diagonal -> merged candidate list ->
                 // columns of A -> fold in L[:, :m]
-                m = h_st->stall_m;
+                const int64_t m = h_st->stall_m;
                 ++refills;
                 pchol_topc_kernel<<<1, 1024, 0, s>>>(diag, nl, row0, pos, m, LA_C, my_list);
                 status = comm_allgather(ctx->comm, my_list, all_lists, LA_LCAP * sizeof(Cand), s);
@@ -711,8 +787,10 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
                     status = dgemm(false, LA_C, nl, m, -1.0, Lc, ld_lc, Lt, ld, 1.0, panel, nl, false, s);
                     if (status != MLFFPC_OK) break;
                 }
-                m0 = m;
-                e2 = cudaMemsetAsync(&st->stalled, 0, sizeof(int), s);
+                h_val[0] = m;
+                e2 = cudaMemcpyAsync(&st->m0, h_val, sizeof(long long), cudaMemcpyHostToDevice, s);
+                if (e2 == cudaSuccess) e2 = cudaMemsetAsync(&st->stalled, 0, sizeof(int), s);
+                if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s);  // h_val is reused by the next rebuild
                 if (e2 != cudaSuccess) { status = cuda_fail(e2, "pchol clear stall", __FILE__, __LINE__); break; }
             }
             if (status == MLFFPC_OK && h_flag_la == 0) {
@@ -721,7 +799,14 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
                 const cudaError_t e3 = cudaStreamSynchronize(s);
                 if (e3 != cudaSuccess) status = cuda_fail(e3, "pchol end", __FILE__, __LINE__);
             }
+            if (pv_on) {  // hand the channel's counters back to the host-side bookkeeping (identical on every rank)
+                ctx->peer->epoch = h_st->epoch > ctx->peer->epoch ? h_st->epoch : ctx->peer->epoch;
+                ctx->peer->uses[PEER_CH_MSG] = h_st->uses;
+            }
         } while (0);
+        if (gexec) cudaGraphExecDestroy(gexec);
+        for (auto& evq : ev_t)
+            if (evq) cudaEventDestroy(evq);
     }
     for (int64_t m = 0; !la && m < k && status == MLFFPC_OK; ++m) {
         pw.step(m);
@@ -825,7 +910,7 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
         if (e != cudaSuccess) status = cuda_fail(e, "pchol flag readback", __FILE__, __LINE__);
         else h_flag = *(int*)ctx->h_scal;
     }
-    if (step_ms_host) {
+    if (step_ms_host && !la) {
         if (status == MLFFPC_OK)
             for (int64_t m = 0; m < k; ++m) cudaEventElapsedTime(&step_ms_host[m], ev[(size_t)m], ev[(size_t)m + 1]);
         for (auto& e : ev) cudaEventDestroy(e);
