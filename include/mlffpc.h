@@ -136,6 +136,8 @@ int mlffpc_symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full
  *   "gram_mode"       [1]  Gram matrices (mlffpc_syrk_rows) with (hi, lo) accumulation of the k-tile products;
  *                          0 = one running fp64 sum per entry (the round-1 kernel: 188 instead of the reference's 119
  *                          CG iterations on BASELINE.json configs[0])
+ *   "gram_fold"       [1]  k-tiles (16 columns each) of DMMA accumulation per (hi, lo) fold: 1, 2 or 4 (cfg2: 920 / 945 /
+ *                          1124 CG iterations -- the accuracy of E decides, so the default folds every k-tile)
  *   "pairs_kernel"    [0]  pair stage of the matrix-free operator / prediction: 2 = 128 x 64 tiles with a cp.async ring,
  *                          1 = the round-1 kernel (64 x 64 tiles, synchronous staging), 0 = 2 for D >= 64 else 1 (measured)
  *   "peer_kvec", "peer_pivots" [1]  use the mapped peer buffers for the apply's k-vector sum / the pivot-step message

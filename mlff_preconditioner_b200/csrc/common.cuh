@@ -112,6 +112,8 @@ struct mlffpc_ctx {
     bool assemble_legacy = false;  // option "assemble_legacy": one CTA per 3N x 3N block (the first-generation kernel)
     int gram_mode = 1;             // option "gram_mode": 1 (default) = Gram matrices with (hi, lo) accumulation of the k-tile
                                    // products (gramdd.cu); 0 = one running fp64 sum per entry (the round-1 kernel)
+    int symop_multi = 1;           // option "symop_multi": 1 = all tiles of a rank in one persistent launch, 0 = tile by tile
+    int gram_fold = 0;             // option "gram_fold": k-tiles (16 columns) per (hi, lo) fold: 1 (default; 0 = default), 2 or 4
     int defect_mode = 1;           // option "defect_mode": E = Q Q^T - I from 1 = the DMMA kernel with (hi, lo) k-tile folding,
                                    // 2 = exact products and sums on the FP64 vector pipe (~7x slower; reference for tests)
     int64_t syrk_chunk = 0;        // option "syrk_chunk": > 0 = Gram matrices by column chunks with Kahan-summed partials (diagnostics)
@@ -120,7 +122,7 @@ struct mlffpc_ctx {
     bool pchol_graph = true;       // option "pchol_graph": replay a chunk of pivot steps as one CUDA graph when no NCCL call sits inside
     bool pchol_lookahead = true;   // option "pchol_lookahead": candidate-panel (blocked) pivoted Cholesky
     long long last_pchol_refills = 0;  // panel rebuilds of the last mlffpc_pchol_build (diagnostics)
-    bool tma_attr_symv = false, tma_attr_rows = false;  // cudaFuncSetAttribute done for this context's device
+    bool tma_attr_symv = false, tma_attr_rows = false, tma_attr_multi = false;  // cudaFuncSetAttribute done for this context's device
     double* rows_ws = nullptr;     // scratch of the TMA row-strip GEMV (precon.cu), owned by the context
     int64_t rows_ws_len = 0;
     int pairs_kernel = 0;          // option "pairs_kernel": 0 = by descriptor length (default), 2 = 128 x 64 tiles + cp.async ring, 1 = round-1 kernel
@@ -194,6 +196,16 @@ bool symv_tma_usable(const double* K, int64_t ld, int64_t nr);
 int symv_tile_tma(mlffpc_ctx* ctx, const double* K, int64_t ld, int64_t nr, int64_t nc, int diag, int packed,
                   const double* xr, const double* xc, double* wsd, double* out_c, double* out_r,
                   const double* x_shift, double alpha, double shift, cudaStream_t s);
+// all tiles of a rank in one persistent launch (symtma.cu); tile 0 = the diagonal tile
+struct SymTileIn {
+    const double* K;
+    int64_t ld, nr, nc, row_off;
+    int diag, packed;
+    const double* xr;
+    const double* xc;
+    double* out_c;
+};
+int symv_tiles_tma(mlffpc_ctx* ctx, int ntiles, const SymTileIn* in, double* wsd, cudaStream_t s);
 // explicit rectangle K[points i_pt0:i_pt1, points j_pt0:j_pt1] -> out; packed = 0: row-major with leading
 // dimension ld; packed = 1 (square diagonal tiles): the band layout of symlayout.cuh, entries right of a
 // band's pitch are not stored
@@ -229,5 +241,6 @@ int gram_dd(mlffpc_ctx* ctx, const double* X, int64_t m, int64_t n_cols, int64_t
 int dgemm(bool transB, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only,
           cudaStream_t s, int nsplit = 1, int64_t c_zstride = 0);
+int dgemm_split_k(int64_t m, int64_t n, int64_t k, int num_sms);
 
 }  // namespace mlffpc

@@ -255,6 +255,8 @@ int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value) {
     if (nm == "peer_kvec") { ctx->peer_kvec = value != 0; return MLFFPC_OK; }
     if (nm == "tma_rows") { ctx->tma_rows = value != 0 ? 1 : 0; return MLFFPC_OK; }
     if (nm == "defect_mode") { ctx->defect_mode = value == 2 ? 2 : 1; return MLFFPC_OK; }
+    if (nm == "symop_multi") { ctx->symop_multi = value != 0 ? 1 : 0; return MLFFPC_OK; }
+    if (nm == "gram_fold") { ctx->gram_fold = (value == 1 || value == 2 || value == 4) ? (int)value : 0; return MLFFPC_OK; }
     if (nm == "gram_mode") { ctx->gram_mode = value != 0 ? 1 : 0; return MLFFPC_OK; }
     if (nm == "syrk_chunk") { ctx->syrk_chunk = value > 0 ? value : 0; return MLFFPC_OK; }
     if (nm == "precon_accuracy") { ctx->precon_accuracy = (int)value; return MLFFPC_OK; }

@@ -189,25 +189,94 @@ static int launch_dgemm(int64_t m, int64_t n, int64_t k, double alpha, const dou
     return MLFFPC_OK;
 }
 
+// Tile shapes.  The square ones serve the big products; the narrow ones keep a product with few output columns
+// (the contraction of the matrix-free operator: n = D + 1 = 37 ... 211) from padding n up to 64 / 128.
+enum GemmShapeId { GS_128x128_16W, GS_128x128_8W, GS_128x64, GS_64x128, GS_128x112, GS_128x80, GS_256x40 };
+
+static GemmShapeId gemm_pick_shape(int64_t m, int64_t n) {
+    static const bool warps16 = [] { const char* e = getenv("MLFFPC_DGEMM16"); return !(e && e[0] == '0'); }();
+    static const bool narrow_tiles = [] { const char* e = getenv("MLFFPC_DGEMM_NARROW"); return !(e && e[0] == '0'); }();
+    if (narrow_tiles && n <= 40 && m >= 512) return GS_256x40;
+    if (n <= 64) return GS_128x64;
+    if (m <= 64) return GS_64x128;  // few rows, many columns (the look-ahead panel update, TRSM tails)
+    if (narrow_tiles && n <= 512) {  // least padding of n; ties go to the wider tile
+        auto padded = [n](int64_t bn) { return (n + bn - 1) / bn * bn; };
+        const int64_t p128 = padded(128), p112 = padded(112), p80 = padded(80);
+        if (p112 < p128 && p112 <= p80) return GS_128x112;
+        if (p80 < p128 && p80 < p112) return GS_128x80;
+    }
+    // 16 warps with 32x32 warp tiles on the 128x128 tile (twice the warps per SM to cover the
+    // shared-load -> DMMA latency): 29.0 vs 27.0 TFLOP/s at 8192^3; MLFFPC_DGEMM16=0 selects the 8-warp kernel
+    return warps16 ? GS_128x128_16W : GS_128x128_8W;
+}
+
+template <int BM, int BN, int WARPS_M, int WARPS_N>
+static int launch_shape(bool transB, bool vec2, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                        const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only,
+                        cudaStream_t s, int nsplit, int64_t c_zstride) {
+    if (transB)
+        return vec2 ? launch_dgemm<BM, BN, WARPS_M, WARPS_N, true, true>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride)
+                    : launch_dgemm<BM, BN, WARPS_M, WARPS_N, true, false>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride);
+    return vec2 ? launch_dgemm<BM, BN, WARPS_M, WARPS_N, false, true>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride)
+                : launch_dgemm<BM, BN, WARPS_M, WARPS_N, false, false>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride);
+}
+
+template <int BM, int BN, int WARPS_M, int WARPS_N>
+static int shape_ctas_per_sm() {  // resident CTAs per SM of the non-transposed, 16-byte staged variant
+    using SM = GemmSmem<BM, BN, false>;
+    auto kern = dgemm_kernel<BM, BN, WARPS_M, WARPS_N, false, true>;
+    int nb = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS_M * WARPS_N * 32, SM::BYTES) != cudaSuccess || nb < 1) {
+        cudaGetLastError();
+        nb = 1;
+    }
+    return nb;
+}
+
+#define MLFFPC_GEMM_SHAPES(X)                                                                                     \
+    X(GS_128x128_16W, 128, 128, 4, 4) X(GS_128x128_8W, 128, 128, 2, 4) X(GS_128x64, 128, 64, 4, 2)              \
+    X(GS_64x128, 64, 128, 2, 4) X(GS_128x112, 128, 112, 8, 2) X(GS_128x80, 128, 80, 8, 2) X(GS_256x40, 256, 40, 16, 1)
+
 int dgemm(bool transB, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only,
           cudaStream_t s, int nsplit, int64_t c_zstride) {
     if (m <= 0 || n <= 0) return MLFFPC_OK;
     if (nsplit < 1) nsplit = 1;
     const bool vec2 = (lda % 2 == 0) && (ldb % 2 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
-    const bool narrow = (n <= 64);
-    const bool flat = (m <= 64) && !narrow;  // few rows, many columns (the look-ahead panel update, TRSM tails)
-    // 16 warps with 32x32 warp tiles on the 128x128 tile (twice the warps per SM to cover the
-    // shared-load -> DMMA latency): 29.0 vs 27.0 TFLOP/s at 8192^3; MLFFPC_DGEMM16=0 selects the 8-warp kernel
-    static const bool warps16 = [] { const char* e = getenv("MLFFPC_DGEMM16"); return !(e && e[0] == '0'); }();
-#define MLFFPC_GEMM_DISPATCH(TB, V2)                                                                      \
-    (narrow ? launch_dgemm<128, 64, 4, 2, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride) \
-     : flat ? launch_dgemm<64, 128, 2, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride) \
-     : warps16 ? launch_dgemm<128, 128, 4, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride) \
-            : launch_dgemm<128, 128, 2, 4, TB, V2>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride))
-    if (transB) return vec2 ? MLFFPC_GEMM_DISPATCH(true, true) : MLFFPC_GEMM_DISPATCH(true, false);
-    return vec2 ? MLFFPC_GEMM_DISPATCH(false, true) : MLFFPC_GEMM_DISPATCH(false, false);
-#undef MLFFPC_GEMM_DISPATCH
+    switch (gemm_pick_shape(m, n)) {
+#define X(ID, BM, BN, WM, WN) \
+    case ID: return launch_shape<BM, BN, WM, WN>(transB, vec2, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only, s, nsplit, c_zstride);
+        MLFFPC_GEMM_SHAPES(X)
+#undef X
+    }
+    return MLFFPC_ERR_INVALID;
+}
+
+// Split-K factor for a product with few output tiles and a long k (C = A[m,k] B[k,n], row-major B): the number of
+// slices that fills whole waves of the tile shape dgemm() will pick, each slice keeping >= 512 columns of k.
+int dgemm_split_k(int64_t m, int64_t n, int64_t k, int num_sms) {
+    int bm = 128, bn = 128, occ = 1;
+    switch (gemm_pick_shape(m, n)) {
+#define X(ID, BM, BN, WM, WN) \
+    case ID: { static const int o = shape_ctas_per_sm<BM, BN, WM, WN>(); bm = BM; bn = BN; occ = o; break; }
+        MLFFPC_GEMM_SHAPES(X)
+#undef X
+    }
+    const int64_t tiles = ((m + bm - 1) / bm) * ((n + bn - 1) / bn);
+    const int64_t slots = (int64_t)num_sms * occ;
+    int64_t max_ns = k / 512;
+    if (max_ns > 32) max_ns = 32;
+    if (max_ns < 1) max_ns = 1;
+    int best = 1;
+    double best_eff = -1.0;
+    for (int64_t ns = 1; ns <= max_ns; ++ns) {
+        const int64_t ctas = tiles * ns, waves = (ctas + slots - 1) / slots;
+        // efficiency of the last wave, discounted when the grid does not fill the GPU once
+        const double eff = (double)ctas / (double)(waves * slots);
+        if (eff > best_eff + 0.01) { best_eff = eff; best = (int)ns; }
+    }
+    return best;
 }
 
 // ---- SYRK helpers ---------------------------------------------------------------------------
@@ -426,13 +495,17 @@ int mlffpc_trsm_rows(mlffpc_ctx* ctx, const double* Lf, int64_t m, int64_t ldl, 
     MLFFPC_REQUIRE(ctx && Lf && X && m > 0 && ldl >= m && n_cols >= 0 && ldx >= n_cols, "trsm_rows: bad argument");
     if (n_cols == 0) return MLFFPC_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    // Two-level blocking: inside an outer panel of TRSM_OB rows the 32-row diagonal solves update only the
-    // rest of that panel (K = 32 GEMMs over <= TRSM_OB rows); everything below the panel is updated once
-    // with a K = TRSM_OB GEMM, which is DMMA-bound instead of streaming all remaining rows 8 times.
+    // Two-level blocking, left-looking at the outer level: the TRSM_OB rows of a panel first receive the contribution of
+    // ALL solved rows above them in one GEMM with a long k (X[J0:J1] -= Lf[J0:J1, 0:J0] X[0:J0]: every row of X is
+    // written once, where the right-looking order re-read and re-wrote everything below the panel for each k = 256
+    // slab: 21 instead of 29 TFLOP/s); inside the panel the 32-row diagonal solves update only the rest of the panel.
     ProfWindow pw = prof_window("trsm");
     for (int64_t J0 = 0; J0 < m; J0 += TRSM_OB) {
         pw.step(J0 / TRSM_OB);
         const int64_t J1 = (J0 + TRSM_OB < m) ? (J0 + TRSM_OB) : m;
+        if (J0 > 0) {
+            MLFFPC_TRY(dgemm(false, J1 - J0, n_cols, J0, -1.0, Lf + J0 * ldl, ldl, X, ldx, 1.0, X + J0 * ldx, ldx, false, s));
+        }
         for (int64_t j0 = J0; j0 < J1; j0 += TRSM_NB) {
             const int nb = (int)((J1 - j0 < TRSM_NB) ? (J1 - j0) : TRSM_NB);
             trsm_diag_kernel<<<(unsigned)((n_cols + 127) / 128), 128, 0, s>>>(Lf, ldl, j0, nb, X, n_cols, ldx);
@@ -443,12 +516,6 @@ int mlffpc_trsm_rows(mlffpc_ctx* ctx, const double* Lf, int64_t m, int64_t ldl, 
                 MLFFPC_TRY(dgemm(false, rest, n_cols, nb, -1.0, Lf + (j0 + nb) * ldl + j0, ldl, X + j0 * ldx, ldx,
                                  1.0, X + (j0 + nb) * ldx, ldx, false, s));
             }
-        }
-        const int64_t below = m - J1;
-        if (below > 0) {
-            // X[J1:, :] -= Lf[J1:, J0:J1] X[J0:J1, :]
-            MLFFPC_TRY(dgemm(false, below, n_cols, J1 - J0, -1.0, Lf + J1 * ldl + J0, ldl, X + J0 * ldx, ldx, 1.0,
-                             X + J1 * ldx, ldx, false, s));
         }
     }
     pw.end();

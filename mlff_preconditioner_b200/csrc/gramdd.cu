@@ -57,7 +57,7 @@ constexpr size_t GD_SMEM = (size_t)GD_STAGES * 2 * GD_TILE * sizeof(double);
 
 // lower 64 x 64 tiles of X X^T; slice blockIdx.z takes the k-tiles [z * kt_per, (z + 1) * kt_per) and writes its
 // own (hi, lo) pair at offset z * zstride
-template <bool VEC2>
+template <bool VEC2, int FOLD>
 __global__ void __launch_bounds__(GD_THREADS, 2)
 gram_dd_kernel(const double* __restrict__ X, int64_t m, int64_t k, int64_t ldx, double* __restrict__ Whi,
                double* __restrict__ Wlo, int64_t ldw, int64_t kt_per, int64_t zstride) {
@@ -143,7 +143,8 @@ gram_dd_kernel(const double* __restrict__ X, int64_t m, int64_t k, int64_t ldx, 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
-        // fold the 16-term partial products into the unevaluated sums and restart the accumulators
+        // fold the 16 FOLD-term partial products into the unevaluated sums and restart the accumulators
+        if (FOLD > 1 && ((kt + 1) % FOLD) != 0 && kt + 1 < ktiles) continue;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -302,7 +303,14 @@ int gram_dd(mlffpc_ctx* ctx, const double* X, int64_t m, int64_t n_cols, int64_t
     const bool vec2 = (ldx % 2 == 0) && ((uintptr_t)X % 16 == 0);
     int st = MLFFPC_OK;
     do {
-        auto kern = vec2 ? gram_dd_kernel<true> : gram_dd_kernel<false>;
+        // k-tiles per fold (option "gram_fold").  Measured on cfg2 (n = 108 000, profiles/r02k_*): folding every k-tile
+        // 920 CG iterations, every 2nd 945, every 4th 1124 -- the 17 ms per Gram that a longer interval saves cost far
+        // more in iterations, so the default stays 1.
+        int fold = ctx->gram_fold;
+        if (fold == 0) fold = 1;
+        auto kern = fold >= 4 ? (vec2 ? gram_dd_kernel<true, 4> : gram_dd_kernel<false, 4>)
+                  : fold == 2 ? (vec2 ? gram_dd_kernel<true, 2> : gram_dd_kernel<false, 2>)
+                              : (vec2 ? gram_dd_kernel<true, 1> : gram_dd_kernel<false, 1>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GD_SMEM);
         if (e != cudaSuccess) { st = cuda_fail(e, "gram_dd attribute", __FILE__, __LINE__); break; }
         if (tiles > 0x7fffffffLL) { set_error("gram_dd: m = %lld too large", (long long)m); st = MLFFPC_ERR_INVALID; break; }

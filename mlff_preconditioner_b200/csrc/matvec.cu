@@ -71,8 +71,10 @@ mv_pairs_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __restr
             bj[ld4 + u][lrow] = (jok && dok) ? Bmat[(MS + j0 + lrow) * ldb + d] : 0.0;
         }
         __syncthreads();
-#pragma unroll
-        for (int dd = 0; dd < PDC; ++dd) {
+        // a ragged last chunk stops at the next multiple of 4 (D = 36: 16 + 16 + 4 instead of 48 descriptor steps)
+        const int dd_end = (D - dc >= PDC) ? PDC : ((D - dc + 3) & ~3);
+#pragma unroll 4
+        for (int dd = 0; dd < dd_end; ++dd) {
             double xi[4], xv[4], bv[4];
 #pragma unroll
             for (int a = 0; a < 4; ++a) xi[a] = xq[dd][ty * 4 + a];
@@ -179,8 +181,10 @@ mv_pairs2_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __rest
         const double* xq = p2_smem + (size_t)(c % P2_STAGES) * P2_STAGE;
         const double* xj = xq + P2_DC * P2_QS;
         const double* bj = xj + P2_DC * P2_JS;
+        // the last chunk may hold fewer than 16 descriptors: stop at the next multiple of 4 (zero-filled beyond D)
+        const int dd_end = (D - c * P2_DC >= P2_DC) ? P2_DC : ((D - c * P2_DC + 3) & ~3);
 #pragma unroll 4
-        for (int dd = 0; dd < P2_DC; ++dd) {
+        for (int dd = 0; dd < dd_end; ++dd) {
             double xi[8], xv[4], bv[4];
             const double2* q2 = reinterpret_cast<const double2*>(xq + dd * P2_QS + ty * 8);
 #pragma unroll
@@ -310,14 +314,8 @@ static MvWs mv_layout(const mlffpc_ctx* c) {
     int64_t o = 0;
     w.off_bmat = o; o = up(o + 2 * MS * w.ldb * 8);
     w.off_cmat = o; o = up(o + Ml * 2 * MS * 8);
-    // the contraction G = [C1|C2] [X; beta] has few output tiles and a very long k: split k until the grid
-    // covers the GPU about twice
-    const int64_t tiles = ((Ml + 127) / 128) * ((c->D + 1 + 127) / 128);
-    int64_t ns = (2 * (int64_t)c->num_sms + tiles - 1) / tiles;
-    const int64_t max_by_k = (2 * MS) / 512;  // keep >= 512 columns of k per slice
-    if (ns > max_by_k) ns = max_by_k;
-    if (ns > 32) ns = 32;
-    if (ns < 1) ns = 1;
+    // the contraction G = [C1|C2] [X; beta] has few output tiles and a very long k: split k into whole waves
+    const int64_t ns = dgemm_split_k(Ml, c->D + 1, 2 * MS, c->num_sms);
     w.nsplit = (int)ns;
     w.off_g = o;    o = up(o + ns * Ml * w.ldb * 8);
     w.total = o + 256;
@@ -404,12 +402,7 @@ static PredWs pred_layout(const mlffpc_ctx* c, int64_t B) {
     int64_t o = 0;
     w.off_bmat = o; o = up(o + 2 * MS * w.ldb * 8);
     w.off_cmat = o; o = up(o + B * 2 * MS * 8);
-    const int64_t tiles = ((B + 127) / 128) * ((c->D + 1 + 127) / 128);
-    int64_t ns = (2 * (int64_t)c->num_sms + tiles - 1) / tiles;
-    const int64_t max_by_k = (2 * MS) / 512;
-    if (ns > max_by_k) ns = max_by_k;
-    if (ns > 32) ns = 32;
-    if (ns < 1) ns = 1;
+    const int64_t ns = dgemm_split_k(B, c->D + 1, 2 * MS, c->num_sms);
     w.nsplit = (int)ns;
     w.off_g = o; o = up(o + ns * B * w.ldb * 8);
     w.ncb = (int)((MS + PT - 1) / PT);

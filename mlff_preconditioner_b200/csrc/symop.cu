@@ -222,13 +222,10 @@ static SymWs symop_ws_layout(const mlffpc_ctx* c, const std::vector<SymTile>& ti
     SymWs w;
     const int W = c->lay_world;
     w.n_pad = ((c->M + W - 1) / W) * c->dim_i;
-    int64_t max_ws = 0;
-    for (const auto& t : tiles) {
-        const int64_t e = symv_tma_ws_doubles(t.nr, t.nc);
-        if (e > max_ws) max_ws = e;
-    }
+    int64_t sum_ws = 0;  // the one-launch pass keeps the partials of all tiles at once
+    for (const auto& t : tiles) sum_ws += symv_tma_ws_doubles(t.nr, t.nc);
     int64_t o = 0;
-    w.off_tile = o; o = up(o + max_ws * 8);
+    w.off_tile = o; o = up(o + sum_ws * 8);
     w.off_yp = o; o = up(o + (int64_t)W * w.n_pad * 8);
     w.off_q = o;  o = up(o + w.n_pad * 8);
     w.total = o + 512;
@@ -295,11 +292,24 @@ int symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full, doubl
     const bool peer = !partial_out && peer_on(ctx) && ctx->comm.world == W;
     double* yp = partial_out ? partial_out : (peer ? peer_yp_local(ctx) : (double*)(base + w.off_yp));
     MLFFPC_CUDA(cudaMemsetAsync(yp, 0, (size_t)W * w.n_pad * 8, s));
-    for (const auto& t : tiles) {
-        const double* xr = x_full + t.i_pt0 * di;
-        const double* xc = x_full + t.j_pt0 * di;
-        MLFFPC_TRY(symv_tile_tma(ctx, Ksym + t.off, t.ld, t.nr, t.nc, t.diag, t.diag, xr, xc, wt, yp + t.j_pt0 * di,
-                                 yp + t.i_pt0 * di, nullptr, 1.0, 0.0, s));
+    if (ctx->symop_multi && tiles.size() <= 8) {
+        SymTileIn in[8];
+        for (size_t i = 0; i < tiles.size(); ++i) {
+            const SymTile& t = tiles[i];
+            in[i].K = Ksym + t.off; in[i].ld = t.ld; in[i].nr = t.nr; in[i].nc = t.nc;
+            in[i].row_off = (t.i_pt0 - tiles[0].i_pt0) * di;
+            in[i].diag = t.diag; in[i].packed = t.diag;
+            in[i].xr = x_full + t.i_pt0 * di; in[i].xc = x_full + t.j_pt0 * di;
+            in[i].out_c = yp + t.j_pt0 * di;
+        }
+        MLFFPC_TRY(symv_tiles_tma(ctx, (int)tiles.size(), in, wt, s));
+    } else {
+        for (const auto& t : tiles) {
+            const double* xr = x_full + t.i_pt0 * di;
+            const double* xc = x_full + t.j_pt0 * di;
+            MLFFPC_TRY(symv_tile_tma(ctx, Ksym + t.off, t.ld, t.nr, t.nc, t.diag, t.diag, xr, xc, wt, yp + t.j_pt0 * di,
+                                     yp + t.i_pt0 * di, nullptr, 1.0, 0.0, s));
+        }
     }
     if (partial_out) return MLFFPC_OK;
     MLFFPC_REQUIRE(ctx->comm.world == W, "symop_apply: the tile layout (%d ranks) needs a communicator of that size", W);

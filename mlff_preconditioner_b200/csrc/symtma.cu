@@ -24,6 +24,7 @@
 
 namespace mlffpc {
 
+constexpr int STR_COLS = 64, STR_SPLIT = 4;  // reduce kernels: columns per block, strip split
 constexpr int ST_STAGES = 3;
 constexpr int ST_CONSUMERS = 128;  // thread t owns columns (2t, 2t+1) of a unit
 constexpr int ST_THREADS = ST_CONSUMERS + 32;
@@ -209,6 +210,226 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symv_tma_kernel(const SymTmaArg
     }
 }
 
+// ---- all tiles of a rank in ONE persistent launch -----------------------------------------------------------
+// Sharded, a rank owns the diagonal tile of its row block plus (world - 1) / 2 (+ half a) off-diagonal tiles.  Launched
+// one by one they cost three launches and one pipeline fill / drain each -- at 8 ranks 15 launches for ~1 ms of
+// streaming.  Here the unit lists of the tiles are concatenated: CTA b walks global units [b upc, (b + 1) upc) and
+// crosses tile boundaries like it crosses strip boundaries; one reduce kernel then writes every output entry once
+// (diagonal-tile columns also collect the row sums of the off-diagonal tiles, in tile order: same bits as the
+// tile-by-tile passes, which added them in that order).
+constexpr int SYM_MAX_TILES = 8;
+struct SymTileDev {
+    int64_t nr, nc, nstrips, unit_base, ld_ws, row_off;  // row_off: first row of this tile relative to the diagonal tile
+    int diag, packed;
+    const CUtensorMap* tmaps;
+    const double* xr;
+    const double* xc;
+    double* ws;
+    double* rowpart;
+    double* out_c;
+    int64_t blk_base, ncb;  // reduce kernel: first block and number of 64-column blocks of this tile
+};
+struct SymMultiArgs {
+    int ntiles;
+    int64_t units_total, units_per_cta;
+    SymTileDev t[SYM_MAX_TILES];
+};
+
+struct SymCursor {
+    int ti;
+    int64_t s, j, nj;
+};
+__device__ __forceinline__ void sym_cursor_init(const SymTileDev* T, int ntiles, int64_t u0, SymCursor& c) {
+    int ti = 0;
+    while (ti + 1 < ntiles && T[ti + 1].unit_base <= u0) ++ti;
+    const int64_t lu = u0 - T[ti].unit_base;
+    int64_t lo = 0, hi = T[ti].nstrips;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (st_units_before(mid, T[ti].diag, T[ti].nc) <= lu) lo = mid; else hi = mid;
+    }
+    c.ti = ti;
+    c.s = lo;
+    c.j = lu - st_units_before(lo, T[ti].diag, T[ti].nc);
+    c.nj = st_units_in_strip(lo, T[ti].diag, T[ti].nc);
+}
+__device__ __forceinline__ void sym_cursor_next(const SymTileDev* T, int ntiles, SymCursor& c) {
+    if (++c.j < c.nj) return;
+    c.j = 0;
+    if (++c.s == T[c.ti].nstrips) { ++c.ti; c.s = 0; }
+    c.nj = (c.ti < ntiles) ? st_units_in_strip(c.s, T[c.ti].diag, T[c.ti].nc) : 1;
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 1) symv_tma_multi_kernel(const __grid_constant__ SymMultiArgs a) {
+    extern __shared__ unsigned char st_smem_raw[];
+    unsigned char* sm = (unsigned char*)(((uintptr_t)st_smem_raw + 1023) & ~(uintptr_t)1023);
+    double* tiles = (double*)sm;                                   // [STAGES][32][256]
+    unsigned char* small = sm + (size_t)ST_STAGES * ST_STAGE_BYTES;
+    uint64_t* full_bar = (uint64_t*)small;                         // [STAGES]
+    uint64_t* empty_bar = full_bar + ST_STAGES;                    // [STAGES]
+    double* xs = (double*)(small + 64);                            // [32]
+    double* dsum = xs + ST_ROWS;                                   // [32]
+    double* red = dsum + ST_ROWS;                                  // [32][4]
+    SymTileDev* T = (SymTileDev*)(red + ST_ROWS * 4);              // [SYM_MAX_TILES] (dynamic indexing: keep it out of local memory)
+
+    const int tid = threadIdx.x;
+    const int64_t u0 = (int64_t)blockIdx.x * a.units_per_cta;
+    int64_t u1 = u0 + a.units_per_cta;
+    if (u1 > a.units_total) u1 = a.units_total;
+    if (u0 >= u1) return;
+
+    if (tid < a.ntiles) T[tid] = a.t[tid];
+    if (tid == 0) {
+        for (int i = 0; i < ST_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], ST_CONSUMERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int ntiles = a.ntiles;
+    SymCursor c;
+    sym_cursor_init(T, ntiles, u0, c);
+
+    if (tid >= ST_CONSUMERS) {
+        if (tid == ST_CONSUMERS) {  // producer lane
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t u = u0; u < u1; ++u) {
+                const SymTileDev& t = T[c.ti];
+                const CUtensorMap* map = t.packed ? (t.tmaps + c.s / ST_BAND_STRIPS) : t.tmaps;
+                const int row = t.packed ? (int)((c.s % ST_BAND_STRIPS) * ST_ROWS) : (int)(c.s * ST_ROWS);
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], ST_STAGE_BYTES);
+                tma_load_2d(tiles + (size_t)stage * (ST_ROWS * ST_COLS), map, &full_bar[stage], (int)(c.j * ST_COLS), row, policy);
+                if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+                sym_cursor_next(T, ntiles, c);
+            }
+        }
+        return;
+    }
+
+    const int lane = tid & 31, warp = tid >> 5;
+    double acc[ST_ROWS];
+    int stage = 0;
+    uint32_t phase = 0;
+    bool fresh = true;
+    for (int64_t u = u0; u < u1; ++u) {
+        const SymTileDev& t = T[c.ti];
+        const int64_t s = c.s, j = c.j, nj = c.nj;
+        const int64_t r0 = s * ST_ROWS;
+        const int rows = (int)((t.nr - r0 < ST_ROWS) ? (t.nr - r0) : ST_ROWS);
+        if (fresh) {
+            if (tid < ST_ROWS) {
+                xs[tid] = (tid < rows) ? t.xr[r0 + tid] : 0.0;
+                dsum[tid] = 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < ST_ROWS; ++i) acc[i] = 0.0;
+            consumer_bar();
+            fresh = false;
+        }
+        const double* tile = tiles + (size_t)stage * (ST_ROWS * ST_COLS);
+        const int64_t col0 = j * ST_COLS;
+        const int64_t n2 = t.diag ? r0 : t.nc;
+        const int w = (int)((n2 - col0 < ST_COLS) ? (n2 - col0) : ST_COLS);
+        const bool okx = 2 * tid < w, oky = 2 * tid + 1 < w;
+        double2 xv = make_double2(0.0, 0.0);
+        if (okx) xv.x = __ldg(t.xc + col0 + 2 * tid);
+        if (oky) xv.y = __ldg(t.xc + col0 + 2 * tid + 1);
+        mbar_wait(&full_bar[stage], phase);
+        if (okx) {
+            double2 cacc = make_double2(0.0, 0.0);
+            const double2* tp = reinterpret_cast<const double2*>(tile) + tid;
+#pragma unroll
+            for (int i = 0; i < ST_ROWS; ++i) {
+                double2 kv = tp[i * (ST_COLS / 2)];
+                if (!oky) kv.y = 0.0;
+                const double xrow = xs[i];
+                acc[i] = fma(kv.y, xv.y, fma(kv.x, xv.x, acc[i]));
+                cacc.x = fma(kv.x, xrow, cacc.x);
+                cacc.y = fma(kv.y, xrow, cacc.y);
+            }
+            *reinterpret_cast<double2*>(t.ws + s * t.ld_ws + col0 + 2 * tid) = cacc;
+        }
+        if (t.diag && j == nj - 1) {
+            const int r = tid >> 2, cp = tid & 3;
+            double v = 0.0;
+            if (r < rows)
+                for (int cc = cp; cc < rows; cc += 4) v = fma(tile[r * ST_COLS + w + cc], xs[cc], v);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if (cp == 0) dsum[r] = v;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+
+        if (j + 1 == nj || u + 1 == u1) {
+#pragma unroll
+            for (int i = 0; i < ST_ROWS; ++i) {
+                const double v = warp_sum(acc[i]);
+                if (lane == 0) red[i * 4 + warp] = v;
+            }
+            consumer_bar();
+            if (tid < ST_ROWS) {
+                const int64_t first_unit = t.unit_base + st_units_before(s, t.diag, t.nc);
+                const int slot = (first_unit / a.units_per_cta == (int64_t)blockIdx.x) ? 0 : 1;
+                const double v = dsum[tid] + ((red[tid * 4 + 0] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]));
+                t.rowpart[(s * 2 + slot) * ST_ROWS + tid] = v;
+            }
+            consumer_bar();
+            fresh = true;
+        }
+        sym_cursor_next(T, ntiles, c);
+    }
+}
+
+// one output entry per thread group: column sums of its tile (+ for the diagonal tile: its own row sums and those of
+// the off-diagonal tiles, tile order)
+__global__ void __launch_bounds__(STR_COLS * STR_SPLIT)
+symv_tma_multi_reduce_kernel(const __grid_constant__ SymMultiArgs a) {
+    __shared__ double red[STR_SPLIT][STR_COLS];
+    const int tc = threadIdx.x % STR_COLS, ts = threadIdx.x / STR_COLS;
+    int ti = 0;
+    while (ti + 1 < a.ntiles && a.t[ti + 1].blk_base <= (int64_t)blockIdx.x) ++ti;
+    const SymTileDev& t = a.t[ti];
+    const int64_t c = ((int64_t)blockIdx.x - t.blk_base) * STR_COLS + tc;
+    double acc = 0.0;
+    if (c < t.nc) {
+        int64_t s = (t.diag ? (c / ST_ROWS + 1) : 0) + ts;
+        const double* p = t.ws + c;
+        for (; s + 7 * STR_SPLIT < t.nstrips; s += 8 * STR_SPLIT) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcs(p + (s + u * STR_SPLIT) * t.ld_ws);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+        for (; s < t.nstrips; s += STR_SPLIT) acc += __ldcs(p + s * t.ld_ws);
+    }
+    red[ts][tc] = acc;
+    __syncthreads();
+    if (ts != 0 || c >= t.nc) return;
+    acc = (red[0][tc] + red[1][tc]) + (red[2][tc] + red[3][tc]);
+    if (t.diag) {
+        const int64_t sr = c / ST_ROWS, i = c % ST_ROWS;
+        acc += t.rowpart[(sr * 2) * ST_ROWS + i] + t.rowpart[(sr * 2 + 1) * ST_ROWS + i];
+        for (int q = 0; q < a.ntiles; ++q) {
+            if (q == ti) continue;
+            const SymTileDev& o = a.t[q];
+            const int64_t r = c - o.row_off;
+            if (r >= 0 && r < o.nr) {
+                const int64_t so = r / ST_ROWS, io = r % ST_ROWS;
+                acc += o.rowpart[(so * 2) * ST_ROWS + io] + o.rowpart[(so * 2 + 1) * ST_ROWS + io];
+            }
+        }
+    }
+    t.out_c[c] = acc;
+}
+
 // ---- one-sided variant: y = A x for a wide matrix with FEW rows (the k x n_local preconditioner factor) ---------
 // Same pipeline (persistent CTAs, TMA-fed 3-stage ring of 32 x 256 units, row sums in registers), no column sums.
 // The register-staged gemv_rows kernel needs rows / 4 CTAs' worth of loads in flight and reaches ~0.76 of the HBM
@@ -317,7 +538,6 @@ __global__ void rows_tma_reduce_kernel(const double* __restrict__ rowpart, int n
 }
 
 // columns: out_c[c] = post( [diag: rowsum(c)] + sum_{s >= s_min(c)} ws[s, c] );  rows (off-diagonal): out_r[r] += rowsum(r)
-constexpr int STR_COLS = 64, STR_SPLIT = 4;
 __global__ void __launch_bounds__(STR_COLS * STR_SPLIT)
 symv_tma_reduce_kernel(const double* __restrict__ rowpart, const double* __restrict__ ws, int64_t ld_ws, int64_t nr,
                        int64_t nc, int64_t nstrips, int diag, double* __restrict__ out_c, double* __restrict__ out_r,
@@ -562,6 +782,54 @@ int symv_tile_tma(mlffpc_ctx* ctx, const double* K, int64_t ld, int64_t nr, int6
     const int64_t nrb = diag ? 0 : (nr + STR_COLS * STR_SPLIT - 1) / (STR_COLS * STR_SPLIT);
     symv_tma_reduce_kernel<<<(unsigned)(ncb + nrb), STR_COLS * STR_SPLIT, 0, s>>>(
         a.rowpart, a.ws, a.ld_ws, nr, nc, a.nstrips, diag, out_c, out_r, x_shift, alpha, shift);
+    MLFFPC_LAUNCH_CHECK();
+    return MLFFPC_OK;
+}
+
+// All tiles of a rank in one pass (tile 0 must be the diagonal tile; the others' rows lie inside its row block).
+//   out_c of tile i receives its column sums; the diagonal tile's out_c also the row sums of every tile.
+int symv_tiles_tma(mlffpc_ctx* ctx, int ntiles, const SymTileIn* in, double* wsd, cudaStream_t s) {
+    MLFFPC_REQUIRE(ntiles >= 1 && ntiles <= SYM_MAX_TILES && in[0].diag, "symv_tiles: bad tile list");
+    SymMultiArgs a;
+    a.ntiles = ntiles;
+    int64_t units = 0, max_in_strip = 1, ws_off = 0, rp_total = 0, blk = 0;
+    for (int i = 0; i < ntiles; ++i) {
+        SymTileDev& t = a.t[i];
+        MLFFPC_TRY(get_tmaps(in[i].K, in[i].ld, in[i].nr, in[i].packed, s, &t.tmaps));
+        t.nr = in[i].nr; t.nc = in[i].nc; t.diag = in[i].diag; t.packed = in[i].packed;
+        t.nstrips = (t.nr + ST_ROWS - 1) / ST_ROWS;
+        t.ld_ws = ((t.nc + 1) & ~(int64_t)1) + ST_COLS;
+        t.unit_base = units;
+        units += st_units_before(t.nstrips, t.diag, t.nc);
+        const int64_t mis = st_units_in_strip(t.nstrips - 1, t.diag, t.nc);
+        if (mis > max_in_strip) max_in_strip = mis;
+        t.row_off = in[i].row_off;
+        t.xr = in[i].xr; t.xc = in[i].xc; t.out_c = in[i].out_c;
+        t.ws = wsd + ws_off;
+        ws_off += t.nstrips * t.ld_ws;
+        rp_total += t.nstrips * 2 * ST_ROWS;
+        t.ncb = (t.nc + STR_COLS - 1) / STR_COLS;
+        t.blk_base = blk;
+        blk += t.ncb;
+    }
+    double* rp = wsd + ws_off;
+    for (int i = 0; i < ntiles; ++i) { a.t[i].rowpart = rp; rp += a.t[i].nstrips * 2 * ST_ROWS; }
+    for (int i = ntiles; i < SYM_MAX_TILES; ++i) a.t[i] = a.t[0];
+    a.units_total = units;
+    int64_t ncta = units / max_in_strip;
+    if (ncta > ctx->num_sms) ncta = ctx->num_sms;
+    if (ncta < 1) ncta = 1;
+    a.units_per_cta = (units + ncta - 1) / ncta;
+    if (a.units_per_cta < max_in_strip) a.units_per_cta = max_in_strip;
+    ncta = (units + a.units_per_cta - 1) / a.units_per_cta;
+    MLFFPC_CUDA(cudaMemsetAsync(wsd + ws_off, 0, (size_t)rp_total * 8, s));
+    if (!ctx->tma_attr_multi) {
+        MLFFPC_CUDA(cudaFuncSetAttribute(symv_tma_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+        ctx->tma_attr_multi = true;
+    }
+    symv_tma_multi_kernel<<<(unsigned)ncta, ST_THREADS, ST_SMEM, s>>>(a);
+    MLFFPC_LAUNCH_CHECK();
+    symv_tma_multi_reduce_kernel<<<(unsigned)blk, STR_COLS * STR_SPLIT, 0, s>>>(a);
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;
 }

@@ -137,6 +137,36 @@ def test_symmetric_storage_is_half_and_matches(full):
     del Ksym
 
 
+def test_one_launch_tile_pass_equals_tile_by_tile(full):
+    """Sharded symmetric operator (emulated ranks of an 8- and a 2-rank run at full size): the pass over all tiles of a
+    rank in ONE persistent launch gives bit-identical partial products to the tile-by-tile passes, and the ranks'
+    partials sum to K v."""
+    torch, eng, K = full['torch'], full['eng'], full['K']
+    gen = torch.Generator(device=eng.device).manual_seed(5)
+    v = torch.randn(eng.n, dtype=torch.float64, device=eng.device, generator=gen)
+    try:
+        for world, ranks in ((8, (0, 3, 5, 7)), (2, (0, 1))):
+            total = torch.zeros(eng.n, dtype=torch.float64, device=eng.device) if len(ranks) == world else None
+            for rank in ranks:
+                eng.set_layout(rank, world)
+                Ksym = eng.symop_assemble()
+                eng.set_option('symop_multi', 1)
+                p1 = eng.symop_apply(Ksym, v, partial=True)
+                again = eng.symop_apply(Ksym, v, partial=True)
+                eng.set_option('symop_multi', 0)
+                p0 = eng.symop_apply(Ksym, v, partial=True)
+                assert torch.equal(p1, p0), (world, rank)
+                assert torch.equal(p1, again), (world, rank)
+                if total is not None:
+                    total += p1
+                del Ksym, p0, p1, again
+            if total is not None:
+                assert _rel(total, eng.gemv(K, v, alpha=1.0, shift=0.0)) < 1e-12
+    finally:
+        eng.set_option('symop_multi', 1)
+        eng.set_layout(0, 1)
+
+
 def test_woodbury_at_bench_rank(full):
     """Same Woodbury identity at the rank the benchmark uses (k = 4839: 76 POTRF panels, 19 outer TRSM panels)."""
     torch, eng, inp = full['torch'], full['eng'], full['inp']
