@@ -138,8 +138,9 @@ int mlffpc_symop_apply(mlffpc_ctx* ctx, const double* Ksym, const double* x_full
  *                          CG iterations on BASELINE.json configs[0])
  *   "gram_fold"       [1]  k-tiles (16 columns each) of DMMA accumulation per (hi, lo) fold: 1, 2 or 4 (cfg2: 920 / 945 /
  *                          1124 CG iterations -- the accuracy of E decides, so the default folds every k-tile)
- *   "pairs_kernel"    [0]  pair stage of the matrix-free operator / prediction: 2 = 128 x 64 tiles with a cp.async ring,
- *                          1 = the round-1 kernel (64 x 64 tiles, synchronous staging), 0 = 2 for D >= 64 else 1 (measured)
+ *   "pairs_kernel"    [0]  pair stage of the matrix-free operator / prediction: 1 = 64 x 64 tiles, synchronous staging;
+ *                          2 = 128 x 64 tiles with a cp.async ring (8 x 4 pairs per thread, 8 warps per SM); 3 = 128 x 32
+ *                          tiles (8 x 2 pairs per thread, 16 warps per SM); 0 = 1 for D < 64, else 3 (measured)
  *   "peer_kvec", "peer_pivots" [1]  use the mapped peer buffers for the apply's k-vector sum / the pivot-step message
  *   "tma_rows"        [1]  "T r" of the preconditioner apply on the TMA-fed row-strip kernel (csrc/symtma.cu); 0 = the
  *                          register-staged 4-row GEMV of round 1

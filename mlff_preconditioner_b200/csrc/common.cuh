@@ -125,8 +125,8 @@ struct mlffpc_ctx {
     bool tma_attr_symv = false, tma_attr_rows = false, tma_attr_multi = false;  // cudaFuncSetAttribute done for this context's device
     double* rows_ws = nullptr;     // scratch of the TMA row-strip GEMV (precon.cu), owned by the context
     int64_t rows_ws_len = 0;
-    int pairs_kernel = 0;          // option "pairs_kernel": 0 = by descriptor length (default), 2 = 128 x 64 tiles + cp.async ring, 1 = round-1 kernel
-    bool pairs2_attr = false;
+    int pairs_kernel = 0;          // option "pairs_kernel": 0 = by descriptor length (default), 1 = 64 x 64 tiles, 2 = 128 x 64 + cp.async ring, 3 = 128 x 32, two CTAs per SM
+    int pairs2_attr = 0;           // bit per instantiation of mv_pairs2_kernel whose shared-memory attribute is set
     bool peer_pivots = true;       // option "peer_pivots": pivot-step message over peer memory when mapped
     bool peer_kvec = true;         // option "peer_kvec": k-vector allreduce of the apply over peer memory when mapped
     int tma_rows = 1;              // option "tma_rows": 1 = T r of the preconditioner apply on the TMA row-strip kernel

@@ -250,7 +250,7 @@ int mlffpc_set_option(mlffpc_ctx* ctx, const char* name, int64_t value) {
         return MLFFPC_OK;
     }
     if (nm == "assemble_legacy") { ctx->assemble_legacy = value != 0; return MLFFPC_OK; }
-    if (nm == "pairs_kernel") { ctx->pairs_kernel = (value == 1 || value == 2) ? (int)value : 0; return MLFFPC_OK; }
+    if (nm == "pairs_kernel") { ctx->pairs_kernel = (value >= 1 && value <= 3) ? (int)value : 0; return MLFFPC_OK; }
     if (nm == "peer_pivots") { ctx->peer_pivots = value != 0; return MLFFPC_OK; }
     if (nm == "peer_kvec") { ctx->peer_kvec = value != 0; return MLFFPC_OK; }
     if (nm == "tma_rows") { ctx->tma_rows = value != 0 ? 1 : 0; return MLFFPC_OK; }

@@ -43,6 +43,51 @@ __global__ void mv_prepare_kernel(int64_t MS, int S, int D, int N, int64_t ldb,
     Bmat[(MS + jp) * ldb + d] = beta;
 }
 
+// ---- epilogue arithmetic of a pair -------------------------------------------------------------------------
+// rho^ = q sqrt(s2), e^ = pref exp(-rho^).  With D = 36 the generic sqrt / exp (slow-path calls, range checks) were as
+// many instructions per pair as the descriptor loop itself (ncu, profiles/r02l): these versions assume what holds
+// here -- s2 >= 0 finite, the exponent <= 0 -- and stay within 2 ulp (parity bound of the operator: 1e-10).
+__device__ __forceinline__ double pair_sqrt(double x) {
+    // Newton on y ~ 1/sqrt(x) from the 64-bit rsqrt seed: g -> sqrt(x), h -> 1/(2 sqrt(x))
+    const double xs = fmax(x, 1e-280);  // x = 0 (a point against itself): sqrt = 1e-140 ~ 0 instead of 0 * inf
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
+    double g = xs * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, g, xs);       // last correction on the residual x - g^2
+    return fma(r, h, g);
+}
+__device__ __forceinline__ double pair_exp_neg(double x) {  // exp(x) for x <= 0
+    if (x < -700.0) return 0.0;  // below 1e-304: no contribution (and the exponent arithmetic below stays normal)
+    const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer in the low word
+    const double t = fma(x, 1.4426950408889634074, SHIFT);
+    const int n = __double2loint(t);
+    const double nf = t - SHIFT;
+    double r = fma(nf, -6.93147180369123816490e-01, x);   // Cody-Waite: ln2 = hi + lo
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    // |r| <= ln2 / 2: Taylor to r^13 (remainder 4e-18)
+    double p = 1.6059043836821613e-10;                   // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);                  // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);                 // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);                 // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);                // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);                  // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);                 // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);                 // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);                 // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);                // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);                // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));  // p * 2^n, n >= -1010
+}
+
 constexpr int PT = 64;    // pair tile edge
 constexpr int PDC = 16;   // descriptor chunk
 
@@ -92,19 +137,20 @@ mv_pairs_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __restr
         __syncthreads();
     }
     const double q2 = q * q;
+    const bool interior = (i0 + PT <= Ml) && (j0 + PT <= MS);  // no per-pair bounds tests in full tiles
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int64_t i = i0 + ty * 4 + a;
+        double* crow = Cmat + i * ldc + j0 + tx;
         double esum = 0.0;  // energy: sum_j e^ (1 + rho^) (Delta . beta)   (torchtools.py:268, predict.py:207)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const int64_t j = j0 + tx + 16 * b;
-            if (i >= Ml || j >= MS) continue;
-            const double rho = q * sqrt(s2[a][b]);
-            const double e = pref * exp(-rho);
-            const double c2 = e * (1.0 + rho);
-            Cmat[i * ldc + j] = e * q2 * tt[a][b];
-            Cmat[i * ldc + MS + j] = c2;
+            if (!interior && (i >= Ml || j0 + tx + 16 * b >= MS)) continue;
+            const double rho = q * pair_sqrt(s2[a][b]);
+            const double e = pref * pair_exp_neg(-rho);
+            const double c2 = fma(e, rho, e);
+            crow[16 * b] = e * q2 * tt[a][b];
+            crow[MS + 16 * b] = c2;
             esum = fma(c2, tt[a][b], esum);
         }
         if (Epart) {  // the 16 threads of a row sit in one half-warp
@@ -117,15 +163,19 @@ mv_pairs_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __restr
     }
 }
 
-// Second-generation pair kernel: 128 queries x 64 training rows per CTA, 8 x 4 pairs per thread, descriptor chunks of
-// 16 staged by cp.async into a 3-stage ring (transposed to [d][row] so that a thread's 8 query values and its 2 x 2
-// training values are 128-bit shared loads).  Per descriptor and thread: 8 LDS.128 for 96 FP64 instructions (the first
-// kernel: 12 LDS.64 for 48, and no overlap of the global loads with the arithmetic -- with D = 36 its three chunks
-// were latency-, not pipe-bound).  Same arithmetic per pair as mv_pairs_kernel, same outputs.
-constexpr int P2_TI = 128, P2_TJ = 64, P2_DC = 16, P2_STAGES = 3, P2_THREADS = 256;
-constexpr int P2_QS = P2_TI + 2, P2_JS = P2_TJ + 2;                      // padded row lengths (even: 16-byte aligned pairs)
-constexpr int P2_STAGE = P2_DC * (P2_QS + 2 * P2_JS);                    // doubles per stage
-constexpr size_t P2_SMEM = (size_t)P2_STAGES * P2_STAGE * sizeof(double);
+// Second-generation pair kernel: 128 queries x (16 NB) training rows per CTA, 8 x NB pairs per thread, descriptor chunks
+// of 16 staged by cp.async into a 3-stage ring (transposed to [d][row] so that a thread's 8 query values and its NB
+// training values are 128-bit shared loads).  Same arithmetic per pair as mv_pairs_kernel, same outputs.
+//   NB = 4 (222 registers, 8 warps per SM): 8 LDS.128 for 96 FP64 instructions per descriptor; ncu (r02l, D = 210): FP64
+//          pipe 68 % busy, the rest are fixed-latency waits that two warps per scheduler cannot cover
+//   NB = 2 (<= 128 registers, two CTAs = 16 warps per SM): 6 LDS.128 for 48 FP64 instructions, twice the warps
+constexpr int P2_TI = 128, P2_DC = 16, P2_STAGES = 3, P2_THREADS = 256;
+constexpr int P2_QS = P2_TI + 2;                                          // padded row length (even: 16-byte aligned pairs)
+template <int NB> struct P2Cfg {
+    static constexpr int TJ = 16 * NB, JS = TJ + 2;
+    static constexpr int STAGE = P2_DC * (P2_QS + 2 * JS);                // doubles per stage
+    static constexpr size_t SMEM = (size_t)P2_STAGES * STAGE * sizeof(double);
+};
 
 __device__ __forceinline__ void p2_cp8(void* dst, const void* src, bool ok) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
@@ -133,24 +183,26 @@ __device__ __forceinline__ void p2_cp8(void* dst, const void* src, bool ok) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz));
 }
 
-__global__ void __launch_bounds__(P2_THREADS, 1)
+template <int NB>
+__global__ void __launch_bounds__(P2_THREADS, NB == 2 ? 2 : 1)
 mv_pairs2_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __restrict__ Bmat, int64_t ldb,
                  int64_t MS, int D, double q, double pref, double* __restrict__ Cmat, int64_t ldc,
                  double* __restrict__ Epart, int n_epart) {
+    using C = P2Cfg<NB>;
     extern __shared__ double p2_smem[];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    const int64_t i0 = (int64_t)blockIdx.y * P2_TI, j0 = (int64_t)blockIdx.x * P2_TJ;
-    double s2[8][4], tt[8][4];
+    const int64_t i0 = (int64_t)blockIdx.y * P2_TI, j0 = (int64_t)blockIdx.x * C::TJ;
+    double s2[8][NB], tt[8][NB];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) s2[a][b] = tt[a][b] = 0.0;
+        for (int b = 0; b < NB; ++b) s2[a][b] = tt[a][b] = 0.0;
 
     const int nchunks = (D + P2_DC - 1) / P2_DC;
     auto load_stage = [&](int stage, int c) {
-        double* xq = p2_smem + (size_t)stage * P2_STAGE;
+        double* xq = p2_smem + (size_t)stage * C::STAGE;
         double* xj = xq + P2_DC * P2_QS;
-        double* bj = xj + P2_DC * P2_JS;
+        double* bj = xj + P2_DC * C::JS;
         const int d0 = c * P2_DC;
         // queries: 128 rows x 16 d; a thread copies 8 elements (row = e / 16 keeps the global reads of a warp in rows of 16)
         for (int e = tid; e < P2_TI * P2_DC; e += P2_THREADS) {
@@ -158,11 +210,11 @@ mv_pairs2_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __rest
             const bool ok = (i0 + r < Ml) && (d0 + d < D);
             p2_cp8(xq + d * P2_QS + r, ok ? (Xq + (i0 + r) * D + d0 + d) : Xq, ok);
         }
-        for (int e = tid; e < P2_TJ * P2_DC; e += P2_THREADS) {
+        for (int e = tid; e < C::TJ * P2_DC; e += P2_THREADS) {
             const int r = e / P2_DC, d = e % P2_DC;
             const bool ok = (j0 + r < MS) && (d0 + d < D);
-            p2_cp8(xj + d * P2_JS + r, ok ? (Bmat + (j0 + r) * ldb + d0 + d) : Bmat, ok);
-            p2_cp8(bj + d * P2_JS + r, ok ? (Bmat + (MS + j0 + r) * ldb + d0 + d) : Bmat, ok);
+            p2_cp8(xj + d * C::JS + r, ok ? (Bmat + (j0 + r) * ldb + d0 + d) : Bmat, ok);
+            p2_cp8(bj + d * C::JS + r, ok ? (Bmat + (MS + j0 + r) * ldb + d0 + d) : Bmat, ok);
         }
     };
 #pragma unroll
@@ -178,29 +230,28 @@ mv_pairs2_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __rest
             if (nc < nchunks) load_stage(nc % P2_STAGES, nc);
             asm volatile("cp.async.commit_group;");
         }
-        const double* xq = p2_smem + (size_t)(c % P2_STAGES) * P2_STAGE;
+        const double* xq = p2_smem + (size_t)(c % P2_STAGES) * C::STAGE;
         const double* xj = xq + P2_DC * P2_QS;
-        const double* bj = xj + P2_DC * P2_JS;
+        const double* bj = xj + P2_DC * C::JS;
         // the last chunk may hold fewer than 16 descriptors: stop at the next multiple of 4 (zero-filled beyond D)
         const int dd_end = (D - c * P2_DC >= P2_DC) ? P2_DC : ((D - c * P2_DC + 3) & ~3);
 #pragma unroll 4
         for (int dd = 0; dd < dd_end; ++dd) {
-            double xi[8], xv[4], bv[4];
+            double xi[8], xv[NB], bv[NB];
             const double2* q2 = reinterpret_cast<const double2*>(xq + dd * P2_QS + ty * 8);
 #pragma unroll
             for (int a = 0; a < 4; ++a) { const double2 t = q2[a]; xi[2 * a] = t.x; xi[2 * a + 1] = t.y; }
-            {
-                const double2 t0 = *reinterpret_cast<const double2*>(xj + dd * P2_JS + 2 * tx);
-                const double2 t1 = *reinterpret_cast<const double2*>(xj + dd * P2_JS + 32 + 2 * tx);
-                xv[0] = t0.x; xv[1] = t0.y; xv[2] = t1.x; xv[3] = t1.y;
-                const double2 u0 = *reinterpret_cast<const double2*>(bj + dd * P2_JS + 2 * tx);
-                const double2 u1 = *reinterpret_cast<const double2*>(bj + dd * P2_JS + 32 + 2 * tx);
-                bv[0] = u0.x; bv[1] = u0.y; bv[2] = u1.x; bv[3] = u1.y;
+#pragma unroll
+            for (int h = 0; h < NB / 2; ++h) {  // columns j0 + 32 h + 2 tx + {0, 1}
+                const double2 t0 = *reinterpret_cast<const double2*>(xj + dd * C::JS + 32 * h + 2 * tx);
+                const double2 u0 = *reinterpret_cast<const double2*>(bj + dd * C::JS + 32 * h + 2 * tx);
+                xv[2 * h] = t0.x; xv[2 * h + 1] = t0.y;
+                bv[2 * h] = u0.x; bv[2 * h + 1] = u0.y;
             }
 #pragma unroll
             for (int a = 0; a < 8; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
+                for (int b = 0; b < NB; ++b) {
                     const double dl = xi[a] - xv[b];
                     s2[a][b] = fma(dl, dl, s2[a][b]);
                     tt[a][b] = fma(dl, bv[b], tt[a][b]);
@@ -209,19 +260,21 @@ mv_pairs2_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __rest
     }
     asm volatile("cp.async.wait_group 0;");
     const double q2c = q * q;
+    const bool interior = (i0 + P2_TI <= Ml) && (j0 + C::TJ <= MS);
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
         const int64_t i = i0 + ty * 8 + a;
+        double* crow = Cmat + i * ldc + j0 + 2 * tx;
         double esum = 0.0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int64_t j = j0 + (b >> 1) * 32 + 2 * tx + (b & 1);
-            if (i >= Ml || j >= MS) continue;
-            const double rho = q * sqrt(s2[a][b]);
-            const double e = pref * exp(-rho);
-            const double c2 = e * (1.0 + rho);
-            Cmat[i * ldc + j] = e * q2c * tt[a][b];
-            Cmat[i * ldc + MS + j] = c2;
+        for (int b = 0; b < NB; ++b) {
+            const int jo = (b >> 1) * 32 + (b & 1);  // column offset next to 2 tx
+            if (!interior && (i >= Ml || j0 + 2 * tx + jo >= MS)) continue;
+            const double rho = q * pair_sqrt(s2[a][b]);
+            const double e = pref * pair_exp_neg(-rho);
+            const double c2 = fma(e, rho, e);
+            crow[jo] = e * q2c * tt[a][b];
+            crow[MS + jo] = c2;
             esum = fma(c2, tt[a][b], esum);
         }
         if (Epart) {  // the 16 threads of a row sit in one half-warp
@@ -234,28 +287,47 @@ mv_pairs2_kernel(const double* __restrict__ Xq, int64_t Ml, const double* __rest
     }
 }
 
-// pair stage: the second-generation kernel unless option "pairs_kernel" = 1 selects the first one
+// columns per energy partial: the narrowest pair tile (every kernel writes one partial per tile of its own width; the
+// caller sizes the buffer for 32-column tiles)
+constexpr int P_EPART_COLS = 32;
+
+// pair stage.  Option "pairs_kernel": 1 = first kernel (64 x 64 tiles), 2 = 128 x 64 tiles, 3 = 128 x 32 tiles with two
+// CTAs per SM, 0 = by descriptor length (measured, profiles/r02l-m)
 static int launch_pairs(mlffpc_ctx* ctx, const double* Xq, int64_t Mq, const double* Bmat, int64_t ldb, int64_t MS, int D,
-                        double q, double pref, double* Cmat, double* Epart, cudaStream_t s) {
-    // measured (profiles/r02i_mf_*): the 128 x 64 kernel wins at D = 210 (5.43 vs 5.71 ms on the cfg5 slice) and loses at
-    // D = 36 (0.526 vs 0.490 ms at cfg2, where three 16-wide chunks cannot fill its pipeline): pick by descriptor length
-    const bool first_gen = ctx->pairs_kernel == 1 || (ctx->pairs_kernel == 0 && D < 64);
-    if (first_gen) {
+                        double q, double pref, double* Cmat, double* Epart, int* n_epart_out, cudaStream_t s) {
+    int which = ctx->pairs_kernel;
+    if (which == 0) which = D < 64 ? 1 : 3;
+    if (which == 1) {
         dim3 grid((unsigned)((MS + PT - 1) / PT), (unsigned)((Mq + PT - 1) / PT));
         MLFFPC_REQUIRE(grid.y <= 65535, "pairs: too many query points for this launch shape");
         mv_pairs_kernel<<<grid, 256, 0, s>>>(Xq, Mq, Bmat, ldb, MS, D, q, pref, Cmat, 2 * MS, Epart);
         MLFFPC_LAUNCH_CHECK();
+        if (n_epart_out) *n_epart_out = (int)grid.x;
         return MLFFPC_OK;
     }
-    static_assert(P2_TJ == PT, "the energy partials are laid out per 64-column tile");
-    dim3 grid((unsigned)((MS + P2_TJ - 1) / P2_TJ), (unsigned)((Mq + P2_TI - 1) / P2_TI));
-    MLFFPC_REQUIRE(grid.y <= 65535, "pairs: too many query points for this launch shape");
-    if (!ctx->pairs2_attr) {
-        MLFFPC_CUDA(cudaFuncSetAttribute(mv_pairs2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM));
-        ctx->pairs2_attr = true;
+    if (which == 2) {
+        using C = P2Cfg<4>;
+        dim3 grid((unsigned)((MS + C::TJ - 1) / C::TJ), (unsigned)((Mq + P2_TI - 1) / P2_TI));
+        MLFFPC_REQUIRE(grid.y <= 65535, "pairs: too many query points for this launch shape");
+        if (!(ctx->pairs2_attr & 1)) {
+            MLFFPC_CUDA(cudaFuncSetAttribute(mv_pairs2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+            ctx->pairs2_attr |= 1;
+        }
+        mv_pairs2_kernel<4><<<grid, P2_THREADS, C::SMEM, s>>>(Xq, Mq, Bmat, ldb, MS, D, q, pref, Cmat, 2 * MS, Epart, (int)grid.x);
+        MLFFPC_LAUNCH_CHECK();
+        if (n_epart_out) *n_epart_out = (int)grid.x;
+        return MLFFPC_OK;
     }
-    mv_pairs2_kernel<<<grid, P2_THREADS, P2_SMEM, s>>>(Xq, Mq, Bmat, ldb, MS, D, q, pref, Cmat, 2 * MS, Epart, (int)grid.x);
+    using C = P2Cfg<2>;
+    dim3 grid((unsigned)((MS + C::TJ - 1) / C::TJ), (unsigned)((Mq + P2_TI - 1) / P2_TI));
+    MLFFPC_REQUIRE(grid.y <= 65535, "pairs: too many query points for this launch shape");
+    if (!(ctx->pairs2_attr & 2)) {
+        MLFFPC_CUDA(cudaFuncSetAttribute(mv_pairs2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        ctx->pairs2_attr |= 2;
+    }
+    mv_pairs2_kernel<2><<<grid, P2_THREADS, C::SMEM, s>>>(Xq, Mq, Bmat, ldb, MS, D, q, pref, Cmat, 2 * MS, Epart, (int)grid.x);
     MLFFPC_LAUNCH_CHECK();
+    if (n_epart_out) *n_epart_out = (int)grid.x;
     return MLFFPC_OK;
 }
 
@@ -339,7 +411,7 @@ int matvec_free(mlffpc_ctx* ctx, const double* v, double* y_local, double alpha,
     mv_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(MS, ctx->S, D, N, w.ldb, ctx->Xp, ctx->R_d_desc,
                                                                      ctx->desc_perms, ctx->pair_a, ctx->pair_b, v, nullptr, Bmat);
     MLFFPC_LAUNCH_CHECK();
-    MLFFPC_TRY(launch_pairs(ctx, ctx->R_desc + ctx->pt0 * D, Ml, Bmat, w.ldb, MS, D, q, pref, Cmat, nullptr, s));
+    MLFFPC_TRY(launch_pairs(ctx, ctx->R_desc + ctx->pt0 * D, Ml, Bmat, w.ldb, MS, D, q, pref, Cmat, nullptr, nullptr, s));
     MLFFPC_TRY(dgemm(false, Ml, D + 1, 2 * MS, 1.0, Cmat, 2 * MS, Bmat, w.ldb, 0.0, G, w.ldb, false, s, w.nsplit,
                      Ml * w.ldb));
     int block = 32;
@@ -405,7 +477,7 @@ static PredWs pred_layout(const mlffpc_ctx* c, int64_t B) {
     const int64_t ns = dgemm_split_k(B, c->D + 1, 2 * MS, c->num_sms);
     w.nsplit = (int)ns;
     w.off_g = o; o = up(o + ns * B * w.ldb * 8);
-    w.ncb = (int)((MS + PT - 1) / PT);
+    w.ncb = (int)((MS + P_EPART_COLS - 1) / P_EPART_COLS);  // capacity: the narrowest pair tile
     w.off_epart = o; o = up(o + B * w.ncb * 8);
     w.total = o + 256;
     return w;
@@ -426,12 +498,13 @@ int predict(mlffpc_ctx* ctx, const double* Rq_desc, const double* Rq_d_desc, int
     mv_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(MS, ctx->S, D, N, w.ldb, ctx->Xp, ctx->R_d_desc,
                                                                      ctx->desc_perms, ctx->pair_a, ctx->pair_b, v, beta, Bmat);
     MLFFPC_LAUNCH_CHECK();
-    MLFFPC_TRY(launch_pairs(ctx, Rq_desc, B, Bmat, w.ldb, MS, D, q, pref, Cmat, E_out ? Epart : nullptr, s));
+    int n_epart = 0;
+    MLFFPC_TRY(launch_pairs(ctx, Rq_desc, B, Bmat, w.ldb, MS, D, q, pref, Cmat, E_out ? Epart : nullptr, &n_epart, s));
     MLFFPC_TRY(dgemm(false, B, D + 1, 2 * MS, 1.0, Cmat, 2 * MS, Bmat, w.ldb, 0.0, G, w.ldb, false, s, w.nsplit, B * w.ldb));
     int block = 32;
     while (block < 3 * N && block < 256) block <<= 1;
     mv_epilogue_kernel<<<(unsigned)B, block, 0, s>>>(N, D, 0, Rq_desc, Rq_d_desc, G, w.ldb, w.nsplit, B * w.ldb, nullptr,
-                                                    F_out, 1.0, 0.0, E_out ? Epart : nullptr, w.ncb, E_out);
+                                                    F_out, 1.0, 0.0, E_out ? Epart : nullptr, n_epart, E_out);
     MLFFPC_LAUNCH_CHECK();
     return MLFFPC_OK;
 }

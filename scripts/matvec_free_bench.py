@@ -23,7 +23,7 @@ def main():
     ap.add_argument('--world', type=int, default=8)
     ap.add_argument('--kind', default='aspirin')
     ap.add_argument('--reps', type=int, default=5)
-    ap.add_argument('--pairs-kernel', type=int, default=0, help='library option pairs_kernel (1 = round-1 kernel)')
+    ap.add_argument('--pairs-kernel', type=int, default=0, help="library option pairs_kernel (0 auto, 1, 2, 3)")
     args = ap.parse_args()
     from bench import WORKLOADS, make_inputs
     from mlff_preconditioner_b200.engine import Engine

@@ -139,8 +139,9 @@ def test_symmetric_storage_is_half_and_matches(full):
 
 def test_one_launch_tile_pass_equals_tile_by_tile(full):
     """Sharded symmetric operator (emulated ranks of an 8- and a 2-rank run at full size): the pass over all tiles of a
-    rank in ONE persistent launch gives bit-identical partial products to the tile-by-tile passes, and the ranks'
-    partials sum to K v."""
+    rank in ONE persistent launch is deterministic and agrees with the tile-by-tile passes to rounding (the strips are
+    cut between CTAs at different units, so the row sums are associated differently), and the ranks' partials sum to
+    K v."""
     torch, eng, K = full['torch'], full['eng'], full['K']
     gen = torch.Generator(device=eng.device).manual_seed(5)
     v = torch.randn(eng.n, dtype=torch.float64, device=eng.device, generator=gen)
@@ -155,7 +156,7 @@ def test_one_launch_tile_pass_equals_tile_by_tile(full):
                 again = eng.symop_apply(Ksym, v, partial=True)
                 eng.set_option('symop_multi', 0)
                 p0 = eng.symop_apply(Ksym, v, partial=True)
-                assert torch.equal(p1, p0), (world, rank)
+                assert _rel(p1, p0) < 1e-14, (world, rank)
                 assert torch.equal(p1, again), (world, rank)
                 if total is not None:
                     total += p1

@@ -393,16 +393,18 @@ def test_orthonormal_form_of_the_low_rank_inverse(torch_cuda, golden):
 
 @pytest.mark.parametrize('case', OP_CASES)
 def test_pair_kernels_agree(torch_cuda, golden, case):
-    """The two generations of the matrix-free pair stage (option pairs_kernel) perform the same fused multiply-adds in
-    the same order per pair: identical operator output, ragged tile edges included (D = 36 / 210 / 780, M S = 12 ... 36)."""
+    """The three pair-stage kernels of the matrix-free operator (option pairs_kernel: 64 x 64, 128 x 64 and 128 x 32
+    tiles) perform the same fused multiply-adds in the same order per pair: same operator output to rounding, ragged tile
+    edges included (D = 36 / 210 / 780, M S = 12 ... 36)."""
     torch = torch_cuda
     g = golden(case)
     eng = _engine(g)
     v = torch.as_tensor(g['v'], device=eng.device)
-    eng.set_option('pairs_kernel', 2)
-    out2 = eng.matvec_free(v, alpha=1.0, shift=-float(g['lam'])).cpu().numpy()
-    eng.set_option('pairs_kernel', 1)
-    out1 = eng.matvec_free(v, alpha=1.0, shift=-float(g['lam'])).cpu().numpy()
+    outs = {}
+    for pk in (1, 2, 3):
+        eng.set_option('pairs_kernel', pk)
+        outs[pk] = eng.matvec_free(v, alpha=1.0, shift=-float(g['lam'])).cpu().numpy()
     eng.set_option('pairs_kernel', 0)
-    assert relerr(out2, g['K_op_v']) < TOL and relerr(out1, g['K_op_v']) < TOL
-    assert relerr(out2, out1) < 1e-13
+    for pk in (1, 2, 3):
+        assert relerr(outs[pk], g['K_op_v']) < TOL, pk
+        assert relerr(outs[pk], outs[1]) < 1e-13, pk
