@@ -19,6 +19,8 @@
 
 #include <vector>
 
+#include <time.h>
+
 #include "common.cuh"
 #include "peer.cuh"
 
@@ -609,6 +611,12 @@ int mlffpc_pchol_workspace_bytes(mlffpc_ctx* ctx, int64_t k, int64_t* bytes) {
     return MLFFPC_OK;
 }
 
+static double pchol_wall_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, double* diag,
                        int64_t* index_columns, const int64_t* forced_pivots, float* step_ms_host,
                        void* workspace, int64_t workspace_bytes, void* stream) {
@@ -734,7 +742,13 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
             int64_t done = 0;
             int tcur = 0;
             float carry_ms = 0.f;
+            // MLFFPC_TIMING=1: host wall time of the stepping chunks against the panel rebuilds (both end in a sync)
+            const char* tenv = getenv("MLFFPC_TIMING");
+            const bool t_on = tenv && tenv[0] == '1';
+            double t_rebuild = 0.0, t_begin = t_on ? pchol_wall_ms() : 0.0;
+            int64_t n_chunks = 0;
             while (done < k && status == MLFFPC_OK) {
+                ++n_chunks;
                 pw.step(done);
                 if (gexec) {
                     e = cudaGraphLaunch(gexec, s);
@@ -767,6 +781,7 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
                 // columns of A -> fold in L[:, :m]
                 const int64_t m = h_st->stall_m;
                 ++refills;
+                const double t_r0 = t_on ? pchol_wall_ms() : 0.0;
                 pchol_topc_kernel<<<1, 1024, 0, s>>>(diag, nl, row0, pos, m, LA_C, my_list);
                 status = comm_allgather(ctx->comm, my_list, all_lists, LA_LCAP * sizeof(Cand), s);
                 if (status != MLFFPC_OK) break;
@@ -792,6 +807,12 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
                 if (e2 == cudaSuccess) e2 = cudaMemsetAsync(&st->stalled, 0, sizeof(int), s);
                 if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s);  // h_val is reused by the next rebuild
                 if (e2 != cudaSuccess) { status = cuda_fail(e2, "pchol clear stall", __FILE__, __LINE__); break; }
+                if (t_on) t_rebuild += pchol_wall_ms() - t_r0;
+            }
+            if (t_on && ctx->comm.rank == 0) {
+                const double t_all = pchol_wall_ms() - t_begin;
+                fprintf(stderr, "[mlffpc timing] pchol look-ahead: %lld steps in %lld chunks %.3f ms, %lld panel rebuilds %.3f ms\n",
+                        (long long)done, (long long)n_chunks, t_all - t_rebuild, (long long)refills, t_rebuild);
             }
             if (status == MLFFPC_OK && h_flag_la == 0) {
                 pchol_la_flush_kernel<<<1, 32, 0, s>>>(st, index_columns, pos);
