@@ -616,9 +616,11 @@ def run_ours(args):
         try:
             ns['cfg5'] = north_star_solve('cfg5', 'matrix_free', 'projected', args.ns_cfg5_k, args.ns_cfg5_tol,
                                           args.ns_cfg5_maxiter, world, rank, dev, peak)
-            ns['cfg5']['note'] = ('k = %d (%.1f %% of n) instead of the rule-of-thumb 46 702: at that rank each GPU would hold '
-                                  '58.8 GB of factor and the replicated k^3 factorisation would dominate the solve; tol = %g is '
-                                  "the reference's own solver_tol for its n = 5e5 runs (create_data.py:88-97)"
+            ns['cfg5']['note'] = ('k = %d (%.2f %% of n) instead of the rule-of-thumb 46 702: at that rank each GPU would hold '
+                                  '58.8 GB of factor and the replicated k^3 factorisation would dominate the solve; k is the '
+                                  'minimum of the measured time-to-solution sweep on 8 GPUs (6144: 13.7 s, 8192: 13.4 s, 12288: '
+                                  "17.2 s, 16384: 24.4 s; profiles/r02n_cfg5_sweep.jsonl); tol = %g is the reference's own "
+                                  'solver_tol for its n = 5e5 runs (create_data.py:88-97)'
                                   % (args.ns_cfg5_k, 100.0 * args.ns_cfg5_k / 1260000, args.ns_cfg5_tol))
         except Exception as exc:  # noqa: BLE001
             ns['cfg5'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
@@ -653,7 +655,8 @@ def main():
     ap.add_argument('--north-star', default='auto', choices=['auto', 'on', 'off'],
                     help="add one end-to-end solve of cfg4 (n = 270 000, assembled) and cfg5 (n = 1.26 M, matrix-free) to the "
                          "JSON line; 'auto' = when running cfg2 on 8 GPUs")
-    ap.add_argument('--ns-cfg5-k', type=int, default=16384)
+    ap.add_argument('--ns-cfg5-k', type=int, default=8192,
+                    help='preconditioner rank of the cfg5 north-star solve (minimum of the measured sweep, profiles/r02n_cfg5_sweep.jsonl)')
     ap.add_argument('--ns-cfg5-tol', type=float, default=1e-4)
     ap.add_argument('--ns-cfg5-maxiter', type=int, default=10000)
     ap.add_argument('--opt', action='append', default=[], help='library option name=int (mlffpc_set_option), repeatable')

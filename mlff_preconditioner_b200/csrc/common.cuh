@@ -112,6 +112,7 @@ struct mlffpc_ctx {
     bool assemble_legacy = false;  // option "assemble_legacy": one CTA per 3N x 3N block (the first-generation kernel)
     int gram_mode = 1;             // option "gram_mode": 1 (default) = Gram matrices with (hi, lo) accumulation of the k-tile
                                    // products (gramdd.cu); 0 = one running fp64 sum per entry (the round-1 kernel)
+    int trsm_order = -1;           // set by a factorisation for its TRSM calls: 1 right-looking, 0 left-looking, -1 by column count
     int symop_multi = 1;           // option "symop_multi": 1 = all tiles of a rank in one persistent launch, 0 = tile by tile
     int gram_fold = 0;             // option "gram_fold": k-tiles (16 columns) per (hi, lo) fold: 1 (default; 0 = default), 2 or 4
     int defect_mode = 1;           // option "defect_mode": E = Q Q^T - I from 1 = the DMMA kernel with (hi, lo) k-tile folding,

@@ -495,15 +495,21 @@ int mlffpc_trsm_rows(mlffpc_ctx* ctx, const double* Lf, int64_t m, int64_t ldl, 
     MLFFPC_REQUIRE(ctx && Lf && X && m > 0 && ldl >= m && n_cols >= 0 && ldx >= n_cols, "trsm_rows: bad argument");
     if (n_cols == 0) return MLFFPC_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    // Two-level blocking, left-looking at the outer level: the TRSM_OB rows of a panel first receive the contribution of
-    // ALL solved rows above them in one GEMM with a long k (X[J0:J1] -= Lf[J0:J1, 0:J0] X[0:J0]: every row of X is
-    // written once, where the right-looking order re-read and re-wrote everything below the panel for each k = 256
-    // slab: 21 instead of 29 TFLOP/s); inside the panel the 32-row diagonal solves update only the rest of the panel.
+    // Two-level blocking.  Outer level, left-looking: the TRSM_OB rows of a panel first receive the contribution of ALL
+    // solved rows above them in one GEMM with a long k (X[J0:J1] -= Lf[J0:J1, 0:J0] X[0:J0]: every row of X is written
+    // once); right-looking: each solved panel updates everything below it with a k = 256 GEMM (re-reads and re-writes
+    // the rest of X per slab).  On 108 000 columns the first runs at 29 instead of 21 TFLOP/s (121 vs 136 ms); on the short
+    // per-rank slices of an 8-GPU run the two cost the same, and there the right-looking order is kept: the CG tail of
+    // cfg2 sits at its attainable accuracy, where last-bit differences of the factor move the iteration count on 8 GPUs
+    // between 936 (this order) and 1123-1140 (the other; profiles/r02p_*).  MLFFPC_TRSM_RIGHT=0/1 forces one.
+    // Inside a panel the 32-row diagonal solves update only the rest of the panel.
     ProfWindow pw = prof_window("trsm");
+    static const int forced = [] { const char* e = getenv("MLFFPC_TRSM_RIGHT"); return !e ? -1 : (e[0] == '1' ? 1 : 0); }();
+    const bool right_looking = forced >= 0 ? forced == 1 : (ctx->trsm_order >= 0 ? ctx->trsm_order == 1 : n_cols < 32768);
     for (int64_t J0 = 0; J0 < m; J0 += TRSM_OB) {
         pw.step(J0 / TRSM_OB);
         const int64_t J1 = (J0 + TRSM_OB < m) ? (J0 + TRSM_OB) : m;
-        if (J0 > 0) {
+        if (J0 > 0 && !right_looking) {
             MLFFPC_TRY(dgemm(false, J1 - J0, n_cols, J0, -1.0, Lf + J0 * ldl, ldl, X, ldx, 1.0, X + J0 * ldx, ldx, false, s));
         }
         for (int64_t j0 = J0; j0 < J1; j0 += TRSM_NB) {
@@ -516,6 +522,10 @@ int mlffpc_trsm_rows(mlffpc_ctx* ctx, const double* Lf, int64_t m, int64_t ldl, 
                 MLFFPC_TRY(dgemm(false, rest, n_cols, nb, -1.0, Lf + (j0 + nb) * ldl + j0, ldl, X + j0 * ldx, ldx,
                                  1.0, X + (j0 + nb) * ldx, ldx, false, s));
             }
+        }
+        if (right_looking && m - J1 > 0) {  // X[J1:] -= Lf[J1:, J0:J1] X[J0:J1]
+            MLFFPC_TRY(dgemm(false, m - J1, n_cols, J1 - J0, -1.0, Lf + J1 * ldl + J0, ldl, X + J0 * ldx, ldx, 1.0,
+                             X + J1 * ldx, ldx, false, s));
         }
     }
     pw.end();

@@ -12,8 +12,8 @@
 //   K p       symmetric tile operator: the finish kernel pulls the peers' partial products of its rows (a fused
 //             reduce-scatter) and applies alpha / shift
 //   pivots    the prepare kernel pushes {candidate, factor row}; the update kernel reads the gathered messages
-// Flags are monotonically increasing 64-bit epochs (one per channel and source rank), written with release / read with
-// acquire semantics at system scope.  Without a peer mapping (single GPU, IPC refused) the NCCL path is used.
+// Flags are monotonically increasing 64-bit epochs (one per channel and source rank): a system-scope release fence
+// followed by relaxed flag stores on the producer, relaxed polls followed by an acquire fence on the consumer.  Without a peer mapping (single GPU, IPC refused) the NCCL path is used.
 #pragma once
 #include <stdint.h>
 
@@ -69,18 +69,34 @@ __device__ __forceinline__ void peer_st_release(uint64_t* p, uint64_t v) {
 // loads that must not be served from this SM's L1 (the line may be from an earlier epoch or live on a peer)
 __device__ __forceinline__ double peer_ld(const double* p) { return __ldcg(p); }
 
+__device__ __forceinline__ void peer_st_relaxed(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t peer_ld_relaxed(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 // raise this rank's flag of channel ch on every rank (call from ONE thread after the data stores of the whole grid /
-// CTA are complete and fenced)
+// CTA are complete and fenced).  ONE release fence, then relaxed flag stores that travel together: a st.release per
+// peer waits for the previous peer's store to be acknowledged over NVLink -- 8 ranks, 8 round trips, ~25 us per signal
+// (measured: 42 us per pivot step on 8 GPUs against 10 us on one).
 __device__ __forceinline__ void peer_signal_all(const PeerView& pv, int ch, uint64_t epoch) {
     __threadfence_system();
-    for (int r = 0; r < pv.world; ++r) peer_st_release(pv.flags(r, ch) + pv.rank, epoch);
+    for (int r = 0; r < pv.world; ++r) peer_st_relaxed(pv.flags(r, ch) + pv.rank, epoch);
 }
-// wait until every rank's flag of channel ch in MY buffer has reached epoch (one thread; follow with a barrier)
+// wait until every rank's flag of channel ch in MY buffer has reached epoch (one thread; follow with a barrier): the
+// flags are polled together with relaxed loads, one acquire fence orders the data loads behind them
 __device__ __forceinline__ void peer_wait_all(const PeerView& pv, int ch, uint64_t epoch) {
     const uint64_t* f = pv.flags(pv.rank, ch);
-    for (int r = 0; r < pv.world; ++r)
-        while (peer_ld_acquire(f + r) < epoch) {
-        }
+    bool ok;
+    do {
+        ok = true;
+#pragma unroll
+        for (int r = 0; r < PEER_MAX_RANKS; ++r)
+            if (r < pv.world) ok &= (peer_ld_relaxed(f + r) >= epoch);
+    } while (!ok);
+    __threadfence_system();
 }
 
 // host side (peer.cu)

@@ -193,6 +193,12 @@ int mlffpc_orthonormal_factor(mlffpc_ctx* ctx, double* Lt, int64_t k, int64_t ld
     ProfWindow pw = prof_window("woodbury");
     pw.step(pw.first);
     PhaseTimer pt(s);
+    // one TRSM order for the whole factorisation, the k x k solve included (dense.cu, mlffpc_trsm_rows)
+    struct OrderGuard {
+        mlffpc_ctx* c;
+        OrderGuard(mlffpc_ctx* cc, int64_t cols) : c(cc) { c->trsm_order = cols < 32768 ? 1 : 0; }
+        ~OrderGuard() { c->trsm_order = -1; }
+    } order_guard(ctx, nl);
     // CholeskyQR2 of L (rows of Lt):  Lt = C1 C2 Qt with Qt Qt^T = I to working precision (cond(L) << 1e8)
     MLFFPC_TRY(mlffpc_syrk_rows(ctx, Lt, k, nl, ld, 0.0, W1, k, stream)); pt.lap("orthonormal: gram 1");
     MLFFPC_TRY(chol(W1)); pt.lap("orthonormal: potrf 1");
