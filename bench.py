@@ -83,12 +83,14 @@ class ClockSampler(object):
         self.index, self.samples, self.proc = index, [], None
 
     def start(self):
-        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
+        # one sample per second is enough to see a throttle reason and keeps the driver queries away from the
+        # host-synchronous parts of a step (the pivot loop reads 64 bytes of state every 8 steps)
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,' \
             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
             'clocks_event_reasons.sw_power_cap'
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '1000'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -112,14 +114,14 @@ class ClockSampler(object):
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for s in self.samples:
             f = [x.strip() for x in s.split(',')]
-            if len(f) < 7:
+            if len(f) < 6:
                 continue
             try:
                 sm.append(float(f[0]))
                 mx.append(float(f[1]))
             except ValueError:
                 continue
-            for nm, val in zip(names, f[3:7]):
+            for nm, val in zip(names, f[2:6]):
                 if val.lower().startswith('active'):
                     reasons.add(nm)
         busy = [c for c in sm if c > 0]
