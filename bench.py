@@ -80,7 +80,7 @@ def make_inputs(workload, M_override=None, tol_override=None, k_override=None):
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(object):
     def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.t_mark = index, [], None, 0.0
 
     def start(self):
         # one sample per second is enough to see a throttle reason and keeps the driver queries away from the
@@ -100,7 +100,13 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: only samples taken after this call are reported.  The sampler itself is started
+        before the warm-up steps, because nvidia-smi's start-up (NVML initialisation on an 8-GPU node) disturbs
+        host-synchronous work for about half a second -- it used to land in the second timed step."""
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -112,7 +118,9 @@ class ClockSampler(object):
             pass
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for s in self.samples:
+        for ts, s in self.samples:
+            if ts < self.t_mark:
+                continue
             f = [x.strip() for x in s.split(',')]
             if len(f) < 6:
                 continue
@@ -447,11 +455,12 @@ def run_ours(args):
         out = it.solve_device(task, eng, y_t, frac, 'cholesky', n_ind)
         return it, out
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         one_step()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     launches0 = lib.mlffpc_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
