@@ -32,11 +32,10 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
-// C[m,n] = alpha * A[m,k] * op(B) + beta * C.   BK = 16, 3-stage cp.async pipeline, 256 threads.
+// C[m,n] = alpha * A[m,k] * op(B) + beta * C.   BK = 16, 3-stage cp.async pipeline, 256 or 512 threads.
 // smem strides are == 4 (mod 16) doubles so the m8n8k4 fragment loads are bank-conflict free.
 constexpr int GEMM_BK = 16;
 constexpr int GEMM_STAGES = 3;
-constexpr int GEMM_THREADS = 256;
 
 template <int BM, int BN, bool TRANSB>
 struct GemmSmem {

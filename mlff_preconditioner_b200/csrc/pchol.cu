@@ -840,49 +840,16 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
         pchol_reduce_kernel<<<1, 256, 0, s>>>(partials, prev_parts, my_cand);
         status = comm_allgather(ctx->comm, my_cand, all_cand, sizeof(Cand), s);
         if (status != MLFFPC_OK) break;
-        // (2) pivot, swap, sqrt (+ the pivot's slot in the candidate panel)
+        // (2) pivot, swap, sqrt
         pchol_select_kernel<<<1, 32, 0, s>>>(all_cand, world, m, forced_pivots, diag, row0, nl, index_columns,
-                                             pos, piv_idx, piv_val, flag, la ? cslot : nullptr, slot_dev);
+                                             pos, piv_idx, piv_val, flag, nullptr, slot_dev);
         if (forced_pivots && world > 1) {
             set_error("pchol_build: forced_pivots is a single-GPU diagnostic");
             status = MLFFPC_ERR_UNSUPPORTED;
             break;
         }
         g_launches += 3;
-        if (la) {
-            // the host decides between "step" and "rebuild the panel, then step": one 4-byte read per step
-            cudaError_t e = cudaMemcpyAsync(ctx->h_scal + 8, slot_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-            if (e != cudaSuccess) { status = cuda_fail(e, "pchol slot readback", __FILE__, __LINE__); break; }
-            const int slot = *(int*)(ctx->h_scal + 8);
-            if (slot < 0) {
-                // (2b) rebuild: top rows by residual diagonal -> merged candidate list -> columns of A -> fold in L[:, :m]
-                ++refills;
-                pchol_topc_kernel<<<1, 1024, 0, s>>>(diag, nl, row0, pos, m, LA_C, my_list);
-                status = comm_allgather(ctx->comm, my_list, all_lists, LA_LCAP * sizeof(Cand), s);
-                if (status != MLFFPC_OK) break;
-                int E = 1;
-                while (E < world * LA_LCAP) E <<= 1;
-                pchol_merge_kernel<<<1, 1024, 3 * E * sizeof(double), s>>>(all_lists, world * LA_LCAP, piv_idx, cand_idx,
-                                                                         cslot, slot_dev);
-                g_launches += 2;
-                status = mlffpc_kernel_columns(ctx, cand_idx, LA_C, panel, nl, -1.0, nullptr, 0, (void*)s);
-                if (status != MLFFPC_OK) break;
-                if (m > 0) {
-                    const int64_t ld_lc = (m + 1) & ~(int64_t)1;  // even pitch: the GEMM stages 16-byte copies
-                    pchol_gather_cand_rows_kernel<<<dim3((unsigned)((ld_lc + 255) / 256), LA_C), 256, 0, s>>>(
-                        Lt, ld, m, ld_lc, cand_idx, row0, nl, Lc);
-                    ++g_launches;
-                    status = comm_allreduce_sum(ctx->comm, Lc, (size_t)(LA_C * ld_lc), s);
-                    if (status != MLFFPC_OK) break;
-                    // panel[c, :] -= Lc[c, :m] Lt[:m, :]
-                    status = dgemm(false, LA_C, nl, m, -1.0, Lc, ld_lc, Lt, ld, 1.0, panel, nl, false, s);
-                    if (status != MLFFPC_OK) break;
-                }
-                m0 = m;
-            }
-        }
-        // (3) pivot row of the factor (columns m0 .. m-1), replicated
+        // (3) pivot row of the factor (columns 0 .. m-1; m0 stays 0 in the plain build), replicated
         if (m > m0) {
             pchol_gather_row_kernel<<<(unsigned)((m - m0 + 255) / 256), 256, 0, s>>>(Lt, ld, m0, m, piv_idx, row0, nl, lrow);
             ++g_launches;
@@ -890,14 +857,12 @@ int mlffpc_pchol_build(mlffpc_ctx* ctx, int64_t k, double* Lt, int64_t ld, doubl
             if (world > 1) status = comm_allreduce_sum(ctx->comm, lrow + m0, (size_t)(m - m0), s);
         }
         if (status != MLFFPC_OK) break;
-        // (4) column pi of A = -K on the local rows (plain variant; the panel already holds it otherwise)
-        if (!la) {
-            status = launch_columns_device_col(ctx, piv_idx, col, -1.0, s);
-            if (status != MLFFPC_OK) break;
-        }
-        // (5) Schur update over the factor columns m0 .. m-1, new factor row, residual diagonal, next candidates
-        const double* colsrc = la ? panel : col;
-        const int* slot_ptr = la ? slot_dev : nullptr;
+        // (4) column pi of A = -K on the local rows
+        status = launch_columns_device_col(ctx, piv_idx, col, -1.0, s);
+        if (status != MLFFPC_OK) break;
+        // (5) Schur update over the factor columns 0 .. m-1, new factor row, residual diagonal, next candidates
+        const double* colsrc = col;
+        const int* slot_ptr = nullptr;
         const int ms = pchol_msplit(nl, m - m0, ctx->num_sms);
         if ((nl + (256 / ms) - 1) / (256 / ms) > MLFFPC_MAX_PARTIALS) {
             set_error("pchol_build: n_local too large for the candidate buffer");
