@@ -31,4 +31,50 @@ __host__ __device__ __forceinline__ int64_t st_packed_elems(int64_t nr) {
     return st_band_off(nb - 1) + (nr - (nb - 1) * ST_BAND_ROWS) * st_band_pitch(nb - 1);
 }
 
+// ---- walking the concatenated unit lists of several tiles (the one-launch pass, symtma.cu) ------------------------
+// Tile type T needs: nstrips, nc, unit_base (global index of its first unit), diag.  CTA b owns the global units
+// [b upc, (b + 1) upc); upc >= the longest strip of any tile, so a strip is shared by at most two CTAs: the one that
+// starts it writes row-sum slot 0, the other slot 1.
+struct SymCursor {
+    int ti;
+    int64_t s, j, nj;  // tile, strip, unit within the strip, units of the strip
+};
+template <class T>
+__host__ __device__ __forceinline__ void sym_cursor_init(const T* tiles, int ntiles, int64_t u0, SymCursor& c) {
+    int ti = 0;
+    while (ti + 1 < ntiles && tiles[ti + 1].unit_base <= u0) ++ti;
+    const int64_t lu = u0 - tiles[ti].unit_base;
+    int64_t lo = 0, hi = tiles[ti].nstrips;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (st_units_before(mid, tiles[ti].diag, tiles[ti].nc) <= lu) lo = mid; else hi = mid;
+    }
+    c.ti = ti;
+    c.s = lo;
+    c.j = lu - st_units_before(lo, tiles[ti].diag, tiles[ti].nc);
+    c.nj = st_units_in_strip(lo, tiles[ti].diag, tiles[ti].nc);
+}
+template <class T>
+__host__ __device__ __forceinline__ void sym_cursor_next(const T* tiles, int ntiles, SymCursor& c) {
+    if (++c.j < c.nj) return;
+    c.j = 0;
+    if (++c.s == tiles[c.ti].nstrips) { ++c.ti; c.s = 0; }
+    c.nj = (c.ti < ntiles) ? st_units_in_strip(c.s, tiles[c.ti].diag, tiles[c.ti].nc) : 1;
+}
+// row-sum slot of CTA `cta` for the strip whose first unit has global index first_unit
+__host__ __device__ __forceinline__ int sym_row_slot(int64_t first_unit, int64_t units_per_cta, int64_t cta) {
+    return (first_unit / units_per_cta == cta) ? 0 : 1;
+}
+// units per CTA and CTA count for `units` units on at most max_ctas CTAs
+__host__ __device__ __forceinline__ void sym_cta_split(int64_t units, int64_t max_in_strip, int64_t max_ctas,
+                                                       int64_t* units_per_cta, int64_t* ncta) {
+    int64_t n = units / max_in_strip;
+    if (n > max_ctas) n = max_ctas;
+    if (n < 1) n = 1;
+    int64_t upc = (units + n - 1) / n;
+    if (upc < max_in_strip) upc = max_in_strip;
+    *units_per_cta = upc;
+    *ncta = (units + upc - 1) / upc;
+}
+
 }  // namespace mlffpc

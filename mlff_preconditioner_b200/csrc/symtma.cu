@@ -235,31 +235,6 @@ struct SymMultiArgs {
     SymTileDev t[SYM_MAX_TILES];
 };
 
-struct SymCursor {
-    int ti;
-    int64_t s, j, nj;
-};
-__device__ __forceinline__ void sym_cursor_init(const SymTileDev* T, int ntiles, int64_t u0, SymCursor& c) {
-    int ti = 0;
-    while (ti + 1 < ntiles && T[ti + 1].unit_base <= u0) ++ti;
-    const int64_t lu = u0 - T[ti].unit_base;
-    int64_t lo = 0, hi = T[ti].nstrips;
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (st_units_before(mid, T[ti].diag, T[ti].nc) <= lu) lo = mid; else hi = mid;
-    }
-    c.ti = ti;
-    c.s = lo;
-    c.j = lu - st_units_before(lo, T[ti].diag, T[ti].nc);
-    c.nj = st_units_in_strip(lo, T[ti].diag, T[ti].nc);
-}
-__device__ __forceinline__ void sym_cursor_next(const SymTileDev* T, int ntiles, SymCursor& c) {
-    if (++c.j < c.nj) return;
-    c.j = 0;
-    if (++c.s == T[c.ti].nstrips) { ++c.ti; c.s = 0; }
-    c.nj = (c.ti < ntiles) ? st_units_in_strip(c.s, T[c.ti].diag, T[c.ti].nc) : 1;
-}
-
 __global__ void __launch_bounds__(ST_THREADS, 1) symv_tma_multi_kernel(const __grid_constant__ SymMultiArgs a) {
     extern __shared__ unsigned char st_smem_raw[];
     unsigned char* sm = (unsigned char*)(((uintptr_t)st_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -376,7 +351,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symv_tma_multi_kernel(const __g
             consumer_bar();
             if (tid < ST_ROWS) {
                 const int64_t first_unit = t.unit_base + st_units_before(s, t.diag, t.nc);
-                const int slot = (first_unit / a.units_per_cta == (int64_t)blockIdx.x) ? 0 : 1;
+                const int slot = sym_row_slot(first_unit, a.units_per_cta, (int64_t)blockIdx.x);
                 const double v = dsum[tid] + ((red[tid * 4 + 0] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]));
                 t.rowpart[(s * 2 + slot) * ST_ROWS + tid] = v;
             }
@@ -816,12 +791,8 @@ int symv_tiles_tma(mlffpc_ctx* ctx, int ntiles, const SymTileIn* in, double* wsd
     for (int i = 0; i < ntiles; ++i) { a.t[i].rowpart = rp; rp += a.t[i].nstrips * 2 * ST_ROWS; }
     for (int i = ntiles; i < SYM_MAX_TILES; ++i) a.t[i] = a.t[0];
     a.units_total = units;
-    int64_t ncta = units / max_in_strip;
-    if (ncta > ctx->num_sms) ncta = ctx->num_sms;
-    if (ncta < 1) ncta = 1;
-    a.units_per_cta = (units + ncta - 1) / ncta;
-    if (a.units_per_cta < max_in_strip) a.units_per_cta = max_in_strip;
-    ncta = (units + a.units_per_cta - 1) / a.units_per_cta;
+    int64_t ncta = 1;
+    sym_cta_split(units, max_in_strip, ctx->num_sms, &a.units_per_cta, &ncta);
     MLFFPC_CUDA(cudaMemsetAsync(wsd + ws_off, 0, (size_t)rp_total * 8, s));
     if (!ctx->tma_attr_multi) {
         MLFFPC_CUDA(cudaFuncSetAttribute(symv_tma_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));

@@ -1,5 +1,7 @@
 """CPU: compile (nvcc, host code only) and run the brute-force check of csrc/symlayout.cuh -- the unit enumeration the
-persistent TMA kernel, the tile plan and the packed assembly all share."""
+persistent TMA kernels, the tile plan and the packed assembly all share, and the cursor with which the one-launch pass
+walks the concatenated unit lists of a rank's tiles (every unit once and in order for 1 ... 296 CTAs, at most two CTAs per
+strip, distinct row-sum slots)."""
 import os
 import shutil
 import subprocess
