@@ -35,3 +35,28 @@ def test_ours_arm_fails_loudly_without_cuda():
                           '--warmup', '0'], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, timeout=280)
     assert out.returncode != 0          # no CPU fallback: the product arm must not produce a number without a GPU
     assert out.stdout.strip() == ''
+
+
+def test_clock_sampler_reports_only_the_timed_region():
+    """The sampler is started before the warm-up steps (nvidia-smi's start-up must not land in a timed step); samples
+    taken before mark() are dropped, throttle reasons and the busy-clock median come from the rest."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class _Proc(object):
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    s = bench.ClockSampler(0)
+    s.proc = _Proc()
+    s.samples = [(10.0, '900, 1965, Not Active, Active, Not Active, Not Active'),      # warm-up: thermal flag ignored
+                 (20.0, '1600, 1965, Not Active, Not Active, Not Active, Active'),
+                 (21.0, '1700, 1965, Not Active, Not Active, Not Active, Active'),
+                 (22.0, '0, 1965, Not Active, Not Active, Not Active, Not Active'),      # idle sample: not in the median
+                 (23.0, 'garbage')]
+    s.t_mark = 15.0
+    out = s.stop()
+    assert out['reasons'] == ['sw_power_cap'] and out['sm_mhz'] == 1650.0 and out['sm_max_mhz'] == 1965.0 and out['samples'] == 3
