@@ -498,9 +498,10 @@ int mlffpc_trsm_rows(mlffpc_ctx* ctx, const double* Lf, int64_t m, int64_t ldl, 
     // solved rows above them in one GEMM with a long k (X[J0:J1] -= Lf[J0:J1, 0:J0] X[0:J0]: every row of X is written
     // once); right-looking: each solved panel updates everything below it with a k = 256 GEMM (re-reads and re-writes
     // the rest of X per slab).  On 108 000 columns the first runs at 29 instead of 21 TFLOP/s (121 vs 136 ms); on the short
-    // per-rank slices of an 8-GPU run the two cost the same, and there the right-looking order is kept: the CG tail of
-    // cfg2 sits at its attainable accuracy, where last-bit differences of the factor move the iteration count on 8 GPUs
-    // between 936 (this order) and 1123-1140 (the other; profiles/r02p_*).  MLFFPC_TRSM_RIGHT=0/1 forces one.
+    // per-rank slices of an 8-GPU run the two cost the same, and there the right-looking order is kept: for cfg2 the
+    // measured defect matrix E of the projected form is only just accurate enough, and the last bits of the factor move
+    // the CG iteration count on 8 GPUs between 936 (this order) and 1123-1140 (the other; profiles/r02p_*, DESIGN.md
+    // sections 5 and 10).  MLFFPC_TRSM_RIGHT=0/1 forces one.
     // Inside a panel the 32-row diagonal solves update only the rest of the panel.
     ProfWindow pw = prof_window("trsm");
     static const int forced = [] { const char* e = getenv("MLFFPC_TRSM_RIGHT"); return !e ? -1 : (e[0] == '1' ? 1 : 0); }();
