@@ -390,6 +390,29 @@ def gram_defect(Qt, chunk=16):
     return np.asarray(acc - np.eye(k, dtype=np.longdouble), dtype=float)
 
 
+def gram_defect_split(Qt, head_bits=None):
+    """``E = Qt Qt^T - I`` from an error-free split of the factor (Ozaki-style; a design study for the device, not in
+    the reference and not a library path yet -- DESIGN.md section 10): row i is cut into a head on the fixed-point
+    grid ``2^(e_i - head_bits)`` (e_i: exponent of the row's largest entry) and a tail, ``Qt = Qh + Ql`` exactly.  With
+    ``2 head_bits + log2(n) <= 53`` every product and every partial sum of ``Qh Qh^T`` is an integer multiple of the grid
+    below 2^53: PLAIN fp64 accumulation (any order, e.g. the DMMA pipe without a fold) is exact.  The cross and tail terms
+    are 2^-head_bits smaller, so their ordinary rounding lands far below the 1e-18 the apply needs.
+    Returns (E, head_bits)."""
+    Qt = np.asarray(Qt, dtype=float)
+    k, n = Qt.shape
+    if head_bits is None:
+        head_bits = (53 - int(np.ceil(np.log2(max(n, 2))))) // 2
+    _, e = np.frexp(np.abs(Qt).max(axis=1))            # max|row| = m 2^e, 0.5 <= m < 1
+    g = np.ldexp(1.0, e - head_bits)[:, None]           # grid spacing of the row (a power of two: scaling is exact)
+    Qh = np.rint(Qt / g) * g
+    Ql = Qt - Qh                                        # exact: |Ql| <= g / 2 and both operands share the grid of Qt's low bits
+    Hh = Qh @ Qh.T                                      # exact
+    C = Qh @ Ql.T
+    T = Ql @ Ql.T
+    E = (Hh - np.eye(k)) + (C + C.T) + T
+    return E, head_bits
+
+
 def projected_apply(Qt, Mk, E, lam, a):
     """Projected form of the same inverse (library ``precon_form='projected'``, csrc/precon.cu): the complement uses
     the exact projector onto range(Qt^T) to first order, ``Qt^T (I + E)^{-1} Qt ~ Qt^T (I - E) Qt``:

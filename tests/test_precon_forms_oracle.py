@@ -103,3 +103,36 @@ def test_sharded_twice_projected_apply_equals_unsharded():
         mu = Mk @ (w + w2)
         z = np.concatenate([(p - Qt[:, s].T @ w2) / lam + Qt[:, s].T @ mu for s, p in zip(sl, rp)])
         assert np.linalg.norm(z - ref) <= 1e-9 * np.linalg.norm(ref), cuts
+
+
+def test_defect_from_error_free_split_is_exact_to_1e_21():
+    """Design study for the next device kernel: E = Qt Qt^T - I from an error-free head/tail split
+    of the rows.  The head Gram is EXACT under plain fp64 accumulation in any order (so a tensor-pipe SYRK without any
+    (hi, lo) fold would do), and the result agrees with exact rational arithmetic to ~1e-22 where the fold-per-16-columns
+    scheme of the current kernel is good to ~1e-18 -- the margin the projected apply needs at k ~ 5000."""
+    from fractions import Fraction
+
+    rng = np.random.default_rng(3)
+    k, n = 12, 30000
+    X = rng.standard_normal((k, n)) * np.exp(rng.standard_normal((k, 1)))
+    for _ in range(2):          # CholeskyQR2: rows orthonormal to working precision, |E| ~ 1e-15
+        X = np.linalg.solve(np.linalg.cholesky(X @ X.T), X)
+    E, hb = orc.gram_defect_split(X)
+    assert 2 * hb + int(np.ceil(np.log2(n))) <= 53
+    _, e = np.frexp(np.abs(X).max(axis=1))
+    g = np.ldexp(1.0, e - hb)[:, None]
+    Qh = np.rint(X / g) * g
+    assert np.array_equal(Qh + (X - Qh), X)                                              # the split is error-free
+    H1 = Qh @ Qh.T
+    H2 = sum(Qh[:, c:c + 7] @ Qh[:, c:c + 7].T for c in range(0, n, 7))                   # another summation order
+    H3 = (Qh[:, ::-1] @ Qh[:, ::-1].T)
+    assert np.array_equal(H1, H2) and np.array_equal(H1, H3)                             # exact, hence order-independent
+    E16 = orc.gram_defect(X, 16)
+    worst, worst16 = 0.0, 0.0
+    for (i, j) in ((0, 0), (5, 5), (7, 2), (11, 0), (11, 11)):
+        exact = sum(Fraction(float(a)) * Fraction(float(b)) for a, b in zip(X[i], X[j])) - (1 if i == j else 0)
+        worst = max(worst, abs(float(Fraction(float(E[i, j])) - exact)))
+        worst16 = max(worst16, abs(float(Fraction(float(E16[i, j])) - exact)))
+    assert worst < 1e-21, worst
+    assert worst16 < 3e-17       # the current scheme (emulated): fine for tests, at the edge for k ~ 5000
+    assert np.abs(E).max() < 1e-14 and np.abs(E - E.T).max() == 0.0
